@@ -1,0 +1,485 @@
+/* TEST INFRASTRUCTURE ONLY -- not part of the product, never linked into it.
+ *
+ * OpenCV-free plain-C restatement of the arithmetic behind the reference's per-frame
+ * analysis ops.  The reference files are thin wrappers (cited per function, relative to
+ * /root/reference/scannertools/); the arithmetic itself lives in OpenCV (un-vendored,
+ * "opencv >= 3.4.0", scannertools/README.md:10), whose published algorithm
+ * (modules/video/src/optflowgf.cpp, imgproc color/smooth/resize/histogram, core
+ * mathfuncs) is restated here as documented in SURVEY.md Appendix A/B.
+ *
+ * Pinned by tests/test_oracle.py against goldens generated with cv2 4.13.0
+ * (tests/golden/make_golden.py) and, when cv2 is importable, against cv2 live.
+ *
+ * Build: make -C oracle   ->  oracle/_build/liboracle_restate.so
+ */
+#include <math.h>
+#include <float.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_API __attribute__((visibility("default")))
+
+/* ---- cvRound: round half to even (SSE cvtsd2si) ------------------------------------- */
+static int cv_round(double v) { return (int)nearbyint(v); }
+static int cv_floor_f(float v) { int i = (int)v; return i - (v < (float)i); }
+
+/* ---- gray: cv::cvtColor(COLOR_BGR2GRAY) applied to the RGB frame ----------------------
+ * optical_flow_kernel_cpu.cpp:38-39; SURVEY Appendix B: 15-bit fixed point, c0 = first byte. */
+ORC_API void orc_gray(const uint8_t* rgb, int n_px, uint8_t* gray) {
+  for (int i = 0; i < n_px; ++i) {
+    int c0 = rgb[3 * i], c1 = rgb[3 * i + 1], c2 = rgb[3 * i + 2];
+    gray[i] = (uint8_t)((c0 * 3735 + c1 * 19235 + c2 * 9798 + (1 << 14)) >> 15);
+  }
+}
+
+/* ---- Histogram: histogram_kernel_cpu.cpp:16-46 --------------------------------------- */
+ORC_API void orc_hist_rgb16(const uint8_t* frame, int w, int h, int32_t* out /*[3][16]*/) {
+  memset(out, 0, 48 * sizeof(int32_t));
+  size_t n = (size_t)w * h;
+  for (size_t i = 0; i < n; ++i)
+    for (int j = 0; j < 3; ++j) out[j * 16 + (frame[3 * i + j] >> 4)]++;
+}
+
+/* ---- shot scores: shot_detection.py:14-18 (Chebyshev per channel, summed) ------------- */
+ORC_API void orc_shot_scores(const int32_t* hists /*[n][48]*/, int n, int32_t* S) {
+  if (n > 0) S[0] = 0;
+  for (int i = 1; i < n; ++i) {
+    int32_t s = 0;
+    for (int j = 0; j < 3; ++j) {
+      int32_t m = 0;
+      for (int b = 0; b < 16; ++b) {
+        int32_t d = hists[i * 48 + j * 16 + b] - hists[(i - 1) * 48 + j * 16 + b];
+        if (d < 0) d = -d;
+        if (d > m) m = d;
+      }
+      s += m;
+    }
+    S[i] = s;
+  }
+}
+
+/* ---- FrameDifference: intended semantics of frame_difference_kernel_cpu.cpp:51-61 ----- */
+ORC_API void orc_frame_diff(const uint8_t* prev, const uint8_t* cur, uint8_t* out, size_t n) {
+  for (size_t i = 0; i < n; ++i) out[i] = (uint8_t)(cur[i] - prev[i]);
+}
+
+/* ---- FlowHistogram: flow_histogram_kernel_cpu.cpp:17-56 ------------------------------ */
+static float fast_atan2_deg(float y, float x) {
+  /* OpenCV core fastAtan32f polynomial */
+  const float scale = (float)(180.0 / 3.14159265358979323846);
+  const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale,
+              p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+  float ax = fabsf(x), ay = fabsf(y), a, c, c2;
+  if (ax >= ay) {
+    c = ay / (ax + (float)DBL_EPSILON);
+    c2 = c * c;
+    a = fmaf(fmaf(fmaf(c2, p7, p5), c2, p3), c2, p1) * c;
+  } else {
+    c = ax / (ay + (float)DBL_EPSILON);
+    c2 = c * c;
+    a = 90.f - fmaf(fmaf(fmaf(c2, p7, p5), c2, p3), c2, p1) * c;
+  }
+  if (x < 0) a = 180.f - a;
+  if (y < 0) a = 360.f - a;
+  return a;
+}
+
+ORC_API void orc_polar(const float* flow, int n_px, float* mag, float* deg) {
+  for (int i = 0; i < n_px; ++i) {
+    float x = flow[2 * i], y = flow[2 * i + 1];
+    mag[i] = sqrtf(fmaf(x, x, y * y));
+    deg[i] = fast_atan2_deg(y, x);
+  }
+}
+
+ORC_API void orc_flow_hist(const float* flow, int w, int h, int32_t* out /*[2][64]*/) {
+  memset(out, 0, 128 * sizeof(int32_t));
+  size_t n = (size_t)w * h;
+  const double a_mag = 64.0 / (64.0 - 0.0), a_deg = 64.0 / (360.0 - 0.0);
+  for (size_t i = 0; i < n; ++i) {
+    float x = flow[2 * i], y = flow[2 * i + 1];
+    float m = sqrtf(fmaf(x, x, y * y));
+    float d = fast_atan2_deg(y, x);
+    int im = (int)floor((double)m * a_mag);
+    int id = (int)floor((double)d * a_deg);
+    if (im >= 0 && im < 64) out[im]++;
+    if (id >= 0 && id < 64) out[64 + id]++;
+  }
+}
+
+/* =======================================================================================
+ * Farneback: cv::FarnebackOpticalFlow(3, 0.5, false, 15, 3, 5, 1.2, 0)->calc(prev, next)
+ * optical_flow_kernel_cpu.cpp:15-16,41; algorithm as in SURVEY Appendix A.
+ * ======================================================================================= */
+
+static int reflect101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) {
+    if (i < 0) i = -i;
+    else i = 2 * (n - 1) - i;
+  }
+  return i;
+}
+
+static void gaussian_taps(int ksize, double sigma, float* taps) {
+  if (ksize == 3 && sigma <= 0) { taps[0] = 0.25f; taps[1] = 0.5f; taps[2] = 0.25f; return; }
+  if (sigma <= 0) sigma = 0.3 * ((ksize - 1) * 0.5 - 1) + 0.8;
+  double sum = 0, t[64];
+  for (int i = 0; i < ksize; ++i) {
+    double x = i - (ksize - 1) * 0.5;
+    t[i] = exp(-0.5 / (sigma * sigma) * x * x);
+    sum += t[i];
+  }
+  for (int i = 0; i < ksize; ++i) taps[i] = (float)(t[i] / sum);
+}
+
+/* separable Gaussian, float32, BORDER_REFLECT_101, rows then columns */
+static void gaussian_blur(const float* src, float* dst, int w, int h, int ksize, double sigma) {
+  float taps[64];
+  gaussian_taps(ksize, sigma, taps);
+  int r = ksize / 2;
+  float* tmp = (float*)malloc(sizeof(float) * (size_t)w * h);
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      float s = taps[r] * src[(size_t)y * w + x];
+      for (int k = 1; k <= r; ++k)
+        s += taps[r + k] * (src[(size_t)y * w + reflect101(x - k, w)] + src[(size_t)y * w + reflect101(x + k, w)]);
+      tmp[(size_t)y * w + x] = s;
+    }
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      float s = taps[r] * tmp[(size_t)y * w + x];
+      for (int k = 1; k <= r; ++k)
+        s += taps[r + k] * (tmp[(size_t)reflect101(y - k, h) * w + x] + tmp[(size_t)reflect101(y + k, h) * w + x]);
+      dst[(size_t)y * w + x] = s;
+    }
+  free(tmp);
+}
+
+/* cv::resize INTER_LINEAR for CV_32FC<cn>: horizontal lerp then vertical lerp, float32 */
+static void resize_linear(const float* src, int sw, int sh, float* dst, int dw, int dh, int cn) {
+  if (sw == dw && sh == dh) { memcpy(dst, src, sizeof(float) * (size_t)sw * sh * cn); return; }
+  double scale_x = 1. / ((double)dw / sw), scale_y = 1. / ((double)dh / sh);
+  int* xofs = (int*)malloc(sizeof(int) * dw);
+  float* xa = (float*)malloc(sizeof(float) * dw);
+  for (int dx = 0; dx < dw; ++dx) {
+    float fx = (float)((dx + 0.5) * scale_x - 0.5);
+    int sx = cv_floor_f(fx);
+    fx -= sx;
+    if (sx < 0) { fx = 0; sx = 0; }
+    if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+    xofs[dx] = sx; xa[dx] = fx;
+  }
+  for (int dy = 0; dy < dh; ++dy) {
+    float fy = (float)((dy + 0.5) * scale_y - 0.5);
+    int sy = cv_floor_f(fy);
+    fy -= sy;
+    if (sy < 0) { fy = 0; sy = 0; }
+    if (sy >= sh - 1) { fy = 0; sy = sh - 1; }
+    int sy1 = sy + 1 < sh ? sy + 1 : sy;
+    const float* r0 = src + (size_t)sy * sw * cn;
+    const float* r1 = src + (size_t)sy1 * sw * cn;
+    for (int dx = 0; dx < dw; ++dx) {
+      int sx = xofs[dx], sx1 = sx + 1 < sw ? sx + 1 : sx;
+      float a1 = xa[dx], a0 = 1.f - a1;
+      for (int c = 0; c < cn; ++c) {
+        float h0 = r0[sx * cn + c] * a0 + r0[sx1 * cn + c] * a1;
+        float h1 = r1[sx * cn + c] * a0 + r1[sx1 * cn + c] * a1;
+        dst[((size_t)dy * dw + dx) * cn + c] = h0 * (1.f - fy) + h1 * fy;
+      }
+    }
+  }
+  free(xofs); free(xa);
+}
+
+typedef struct { float g[11], xg[11], xxg[11]; double ig11, ig03, ig33, ig55; } poly_consts;
+
+/* 6x6 inverse by Gauss-Jordan in double (G is SPD and tiny; matches Cholesky to ~1e-16) */
+static void invert6(double A[6][6], double inv[6][6]) {
+  double M[6][12];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) { M[i][j] = A[i][j]; M[i][6 + j] = (i == j); }
+  for (int c = 0; c < 6; ++c) {
+    int p = c;
+    for (int r = c + 1; r < 6; ++r) if (fabs(M[r][c]) > fabs(M[p][c])) p = r;
+    if (p != c) for (int j = 0; j < 12; ++j) { double t = M[c][j]; M[c][j] = M[p][j]; M[p][j] = t; }
+    double d = 1.0 / M[c][c];
+    for (int j = 0; j < 12; ++j) M[c][j] *= d;
+    for (int r = 0; r < 6; ++r) if (r != c) {
+      double f = M[r][c];
+      if (f != 0) for (int j = 0; j < 12; ++j) M[r][j] -= f * M[c][j];
+    }
+  }
+  for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) inv[i][j] = M[i][6 + j];
+}
+
+static void prepare_gaussian(int n, double sigma, poly_consts* pc) {
+  /* FarnebackPrepareGaussian; arrays indexed by |x| (g symmetric, xg antisymmetric) */
+  float gf[32];
+  double s = 0;
+  if (sigma < FLT_EPSILON) sigma = n * 0.3;
+  for (int x = -n; x <= n; ++x) { gf[x + n] = (float)exp(-x * x / (2 * sigma * sigma)); s += gf[x + n]; }
+  s = 1. / s;
+  for (int x = -n; x <= n; ++x) gf[x + n] = (float)(gf[x + n] * s);
+  for (int x = 0; x <= n; ++x) {
+    pc->g[x] = gf[x + n];
+    pc->xg[x] = (float)(x * gf[x + n]);
+    pc->xxg[x] = (float)(x * x * gf[x + n]);
+  }
+  double G[6][6], inv[6][6];
+  memset(G, 0, sizeof(G));
+  for (int y = -n; y <= n; ++y)
+    for (int x = -n; x <= n; ++x) {
+      /* OpenCV evaluates g[y]*g[x]*x*x... in float (float*int -> float), then adds to double */
+      float gg = gf[y + n] * gf[x + n];
+      G[0][0] += gg;
+      G[1][1] += gg * x * x;
+      G[3][3] += gg * x * x * x * x;
+      G[5][5] += gg * x * x * y * y;
+    }
+  G[2][2] = G[0][3] = G[0][4] = G[3][0] = G[4][0] = G[1][1];
+  G[4][4] = G[3][3];
+  G[3][4] = G[4][3] = G[5][5];
+  invert6(G, inv);
+  pc->ig11 = inv[1][1]; pc->ig03 = inv[0][3]; pc->ig33 = inv[3][3]; pc->ig55 = inv[5][5];
+}
+
+ORC_API void orc_poly_consts(int n, double sigma, float* g, float* xg, float* xxg, double* ig /*[4]*/) {
+  poly_consts pc;
+  prepare_gaussian(n, sigma, &pc);
+  for (int i = 0; i <= n; ++i) { g[i] = pc.g[i]; xg[i] = pc.xg[i]; xxg[i] = pc.xxg[i]; }
+  ig[0] = pc.ig11; ig[1] = pc.ig03; ig[2] = pc.ig33; ig[3] = pc.ig55;
+}
+
+/* FarnebackPolyExp: vertical float32, horizontal double accumulators, replicate borders.
+ * dst: h x w x 5 interleaved (as OpenCV) */
+static void poly_exp(const float* src, float* dst, int w, int h, int n, const poly_consts* pc) {
+  float* rowbuf = (float*)malloc(sizeof(float) * (size_t)(w + 2 * n) * 3);
+  float* row = rowbuf + n * 3;
+  for (int y = 0; y < h; ++y) {
+    const float* s0 = src + (size_t)y * w;
+    for (int x = 0; x < w; ++x) { row[x * 3] = s0[x] * pc->g[0]; row[x * 3 + 1] = row[x * 3 + 2] = 0.f; }
+    for (int k = 1; k <= n; ++k) {
+      float g0 = pc->g[k], g1 = pc->xg[k], g2 = pc->xxg[k];
+      const float* a = src + (size_t)(y - k > 0 ? y - k : 0) * w;
+      const float* b = src + (size_t)(y + k < h - 1 ? y + k : h - 1) * w;
+      for (int x = 0; x < w; ++x) {
+        float p = a[x] + b[x];
+        row[x * 3] = row[x * 3] + g0 * p;
+        row[x * 3 + 1] = row[x * 3 + 1] + g1 * (b[x] - a[x]);
+        row[x * 3 + 2] = row[x * 3 + 2] + g2 * p;
+      }
+    }
+    for (int x = 0; x < n * 3; ++x) {
+      row[-1 - x] = row[2 - (x % 3)];
+      row[w * 3 + x] = row[(w - 1) * 3 + (x % 3)];
+    }
+    float* d = dst + (size_t)y * w * 5;
+    for (int x = 0; x < w; ++x) {
+      float g0 = pc->g[0];
+      double b1 = row[x * 3] * g0, b2 = 0, b3 = row[x * 3 + 1] * g0, b4 = 0, b5 = row[x * 3 + 2] * g0, b6 = 0;
+      for (int k = 1; k <= n; ++k) {
+        double tg = row[(x + k) * 3] + row[(x - k) * 3];
+        g0 = pc->g[k];
+        b1 += tg * g0;
+        b4 += tg * pc->xxg[k];
+        b2 += (row[(x + k) * 3] - row[(x - k) * 3]) * pc->xg[k];
+        b3 += (row[(x + k) * 3 + 1] + row[(x - k) * 3 + 1]) * g0;
+        b6 += (row[(x + k) * 3 + 1] - row[(x - k) * 3 + 1]) * pc->xg[k];
+        b5 += (row[(x + k) * 3 + 2] + row[(x - k) * 3 + 2]) * g0;
+      }
+      d[x * 5 + 1] = (float)(b2 * pc->ig11);
+      d[x * 5] = (float)(b3 * pc->ig11);
+      d[x * 5 + 3] = (float)(b1 * pc->ig03 + b4 * pc->ig33);
+      d[x * 5 + 2] = (float)(b1 * pc->ig03 + b5 * pc->ig33);
+      d[x * 5 + 4] = (float)(b6 * pc->ig55);
+    }
+  }
+  free(rowbuf);
+}
+
+/* FarnebackUpdateMatrices over all rows */
+static void update_matrices(const float* R0, const float* R1, const float* flow, float* M, int w, int h) {
+  static const float border[5] = {0.14f, 0.14f, 0.4472f, 0.4472f, 0.4472f};
+  const int BORDER = 5;
+  size_t step1 = (size_t)w * 5;
+  for (int y = 0; y < h; ++y) {
+    const float* r0 = R0 + (size_t)y * w * 5;
+    const float* fl = flow + (size_t)y * w * 2;
+    float* m = M + (size_t)y * w * 5;
+    for (int x = 0; x < w; ++x) {
+      float dx = fl[x * 2], dy = fl[x * 2 + 1];
+      float fx = x + dx, fy = y + dy;
+      int x1 = cv_floor_f(fx), y1 = cv_floor_f(fy);
+      float r2, r3, r4, r5, r6;
+      fx -= x1; fy -= y1;
+      if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
+        const float* p = R1 + (size_t)y1 * step1 + (size_t)x1 * 5;
+        float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+        r2 = a00 * p[0] + a01 * p[5] + a10 * p[step1] + a11 * p[step1 + 5];
+        r3 = a00 * p[1] + a01 * p[6] + a10 * p[step1 + 1] + a11 * p[step1 + 6];
+        r4 = a00 * p[2] + a01 * p[7] + a10 * p[step1 + 2] + a11 * p[step1 + 7];
+        r5 = a00 * p[3] + a01 * p[8] + a10 * p[step1 + 3] + a11 * p[step1 + 8];
+        r6 = a00 * p[4] + a01 * p[9] + a10 * p[step1 + 4] + a11 * p[step1 + 9];
+        r4 = (r0[x * 5 + 2] + r4) * 0.5f;
+        r5 = (r0[x * 5 + 3] + r5) * 0.5f;
+        r6 = (r0[x * 5 + 4] + r6) * 0.25f;
+      } else {
+        r2 = r3 = 0.f;
+        r4 = r0[x * 5 + 2];
+        r5 = r0[x * 5 + 3];
+        r6 = r0[x * 5 + 4] * 0.5f;
+      }
+      r2 = (r0[x * 5] - r2) * 0.5f;
+      r3 = (r0[x * 5 + 1] - r3) * 0.5f;
+      r2 += r4 * dy + r6 * dx;
+      r3 += r6 * dy + r5 * dx;
+      if ((unsigned)(x - BORDER) >= (unsigned)(w - BORDER * 2) || (unsigned)(y - BORDER) >= (unsigned)(h - BORDER * 2)) {
+        float scale = (x < BORDER ? border[x] : 1.f) * (x >= w - BORDER ? border[w - x - 1] : 1.f) *
+                      (y < BORDER ? border[y] : 1.f) * (y >= h - BORDER ? border[h - y - 1] : 1.f);
+        r2 *= scale; r3 *= scale; r4 *= scale; r5 *= scale; r6 *= scale;
+      }
+      m[x * 5] = r4 * r4 + r6 * r6;
+      m[x * 5 + 1] = (r4 + r5) * r6;
+      m[x * 5 + 2] = r5 * r5 + r6 * r6;
+      m[x * 5 + 3] = r4 * r2 + r6 * r3;
+      m[x * 5 + 4] = r6 * r2 + r5 * r3;
+    }
+  }
+}
+
+/* FarnebackUpdateFlow_Blur: 15x15 box (replicate) in double, 2x2 solve; "blur all with the
+ * old M, then update all" (the lagging stripes in OpenCV are semantically this). */
+static void update_flow_blur(const float* R0, const float* R1, float* flow, float* M, int w, int h,
+                             int block, int update) {
+  int m = block / 2;
+  double scale = 1. / (block * block);
+  double* vs = (double*)malloc(sizeof(double) * (size_t)w * 5);
+  for (int y = 0; y < h; ++y) {
+    for (int i = 0; i < w * 5; ++i) vs[i] = 0;
+    for (int dy = -m; dy <= m; ++dy) {
+      int yy = y + dy; yy = yy < 0 ? 0 : (yy > h - 1 ? h - 1 : yy);
+      const float* r = M + (size_t)yy * w * 5;
+      for (int i = 0; i < w * 5; ++i) vs[i] += r[i];
+    }
+    for (int x = 0; x < w; ++x) {
+      double s[5] = {0, 0, 0, 0, 0};
+      for (int dx = -m; dx <= m; ++dx) {
+        int xx = x + dx; xx = xx < 0 ? 0 : (xx > w - 1 ? w - 1 : xx);
+        for (int c = 0; c < 5; ++c) s[c] += vs[xx * 5 + c];
+      }
+      double g11 = s[0] * scale, g12 = s[1] * scale, g22 = s[2] * scale, h1 = s[3] * scale, h2 = s[4] * scale;
+      double idet = 1. / (g11 * g22 - g12 * g12 + 1e-3);
+      flow[((size_t)y * w + x) * 2] = (float)((g11 * h2 - g12 * h1) * idet);
+      flow[((size_t)y * w + x) * 2 + 1] = (float)((g22 * h1 - g12 * h2) * idet);
+    }
+  }
+  free(vs);
+  if (update) update_matrices(R0, R1, flow, M, w, h);
+}
+
+typedef struct {
+  int levels;       /* number of scales actually processed (<= 4 for numLevels = 3) */
+  int w[8], h[8];   /* per scale k */
+} orc_pyr_info;
+
+static int pyramid_levels(int W, int H, int num_levels, double pyr_scale, orc_pyr_info* info) {
+  int k; double scale = 1;
+  for (k = 0; k < num_levels; ++k) {
+    scale *= pyr_scale;
+    if (W * scale < 32 || H * scale < 32) break;
+  }
+  int levels = k;
+  for (k = 0; k <= levels; ++k) {
+    double sc = 1;
+    for (int i = 0; i < k; ++i) sc *= pyr_scale;
+    info->w[k] = cv_round(W * sc);
+    info->h[k] = cv_round(H * sc);
+  }
+  info->levels = levels;
+  return levels;
+}
+
+ORC_API int orc_pyramid_info(int W, int H, int num_levels, double pyr_scale, int* ws, int* hs) {
+  orc_pyr_info info;
+  int l = pyramid_levels(W, H, num_levels, pyr_scale, &info);
+  for (int k = 0; k <= l; ++k) { ws[k] = info.w[k]; hs[k] = info.h[k]; }
+  return l;
+}
+
+/* Stage dumps for stage-by-stage diffing of the CUDA kernels.  dump_level < 0: none.
+ * When dump_level == k the buffers (if non-NULL) receive level k's I (prev image),
+ * R0, R1 (h x w x 5 interleaved) and M after the initial UpdateMatrices. */
+typedef struct {
+  int level;
+  float* I0; float* I1; float* R0; float* R1; float* M0; float* flow_out;
+} orc_dump;
+
+ORC_API void orc_farneback_ex(const uint8_t* gray0, const uint8_t* gray1, int W, int H, float* flow_out,
+                              int num_levels, double pyr_scale, int winsize, int iters, int poly_n,
+                              double poly_sigma, orc_dump* dump) {
+  orc_pyr_info info;
+  int levels = pyramid_levels(W, H, num_levels, pyr_scale, &info);
+  poly_consts pc;
+  prepare_gaussian(poly_n, poly_sigma, &pc);
+  const uint8_t* img[2] = {gray0, gray1};
+  size_t N = (size_t)W * H;
+  float* fimg = (float*)malloc(sizeof(float) * N);
+  float* blur = (float*)malloc(sizeof(float) * N);
+  float* prev_flow = NULL; int pw = 0, ph = 0;
+  for (int k = levels; k >= 0; --k) {
+    double scale = 1;
+    for (int i = 0; i < k; ++i) scale *= pyr_scale;
+    double sigma = (1. / scale - 1) * 0.5;
+    int smooth = cv_round(sigma * 5) | 1;
+    if (smooth < 3) smooth = 3;
+    int w = info.w[k], h = info.h[k];
+    size_t n = (size_t)w * h;
+    float* flow = (float*)malloc(sizeof(float) * n * 2);
+    if (!prev_flow) memset(flow, 0, sizeof(float) * n * 2);
+    else {
+      resize_linear(prev_flow, pw, ph, flow, w, h, 2);
+      float mul = (float)(1. / pyr_scale);
+      for (size_t i = 0; i < n * 2; ++i) flow[i] *= mul;
+    }
+    float* R[2]; float* I = (float*)malloc(sizeof(float) * n);
+    for (int i = 0; i < 2; ++i) {
+      for (size_t p = 0; p < N; ++p) fimg[p] = (float)img[i][p];
+      gaussian_blur(fimg, blur, W, H, smooth, sigma);
+      resize_linear(blur, W, H, I, w, h, 1);
+      R[i] = (float*)malloc(sizeof(float) * n * 5);
+      poly_exp(I, R[i], w, h, poly_n, &pc);
+      if (dump && dump->level == k) {
+        float* dI = i == 0 ? dump->I0 : dump->I1;
+        if (dI) memcpy(dI, I, sizeof(float) * n);
+        float* dR = i == 0 ? dump->R0 : dump->R1;
+        if (dR) memcpy(dR, R[i], sizeof(float) * n * 5);
+      }
+    }
+    float* M = (float*)malloc(sizeof(float) * n * 5);
+    update_matrices(R[0], R[1], flow, M, w, h);
+    if (dump && dump->level == k && dump->M0) memcpy(dump->M0, M, sizeof(float) * n * 5);
+    for (int i = 0; i < iters; ++i) update_flow_blur(R[0], R[1], flow, M, w, h, winsize, i < iters - 1);
+    if (dump && dump->level == k && dump->flow_out) memcpy(dump->flow_out, flow, sizeof(float) * n * 2);
+    free(M); free(R[0]); free(R[1]); free(I);
+    free(prev_flow);
+    prev_flow = flow; pw = w; ph = h;
+  }
+  memcpy(flow_out, prev_flow, sizeof(float) * N * 2);
+  free(prev_flow); free(fimg); free(blur);
+}
+
+/* the reference's fixed parameters: optical_flow_kernel_cpu.cpp:16 */
+ORC_API void orc_farneback(const uint8_t* gray0, const uint8_t* gray1, int W, int H, float* flow_out) {
+  orc_farneback_ex(gray0, gray1, W, H, flow_out, 3, 0.5, 15, 3, 5, 1.2, NULL);
+}
+
+/* OpticalFlow op end to end: optical_flow_kernel_cpu.cpp:27-43 */
+ORC_API void orc_optical_flow_rgb(const uint8_t* rgb0, const uint8_t* rgb1, int W, int H, float* flow_out) {
+  size_t N = (size_t)W * H;
+  uint8_t* g0 = (uint8_t*)malloc(N); uint8_t* g1 = (uint8_t*)malloc(N);
+  orc_gray(rgb0, (int)N, g0); orc_gray(rgb1, (int)N, g1);
+  orc_farneback(g0, g1, W, H, flow_out);
+  free(g0); free(g1);
+}

@@ -1,0 +1,471 @@
+// Histogram, shot-score, FlowHistogram and FrameDifference kernels (sm_100a) + their C ABI.
+//
+// All four are HBM-bound byte/word streaming kernels: each input byte is read exactly once
+// with 16-byte coalesced loads; counting happens in shared memory that is privatised per
+// warp AND per lane (bank == lane), so shared-memory atomics never conflict regardless of
+// image content (constant frames are the worst case for a shared table); one global merge
+// per block.
+//
+// Reference call sites replaced: see include/stb.h.
+#include "stb_rt.h"
+
+namespace stb {
+
+struct PtrAddrU8 {
+  PtrBatch<const uint8_t> t;
+  __device__ __forceinline__ const uint8_t* operator()(unsigned i) const { return t.p[i]; }
+};
+struct StrideAddrU8 {
+  const uint8_t* base;
+  unsigned long long stride;
+  __device__ __forceinline__ const uint8_t* operator()(unsigned i) const { return base + (unsigned long long)i * stride; }
+};
+
+// -------------------------------------------------------------------------------------------
+// RGB histogram, 16 bins/channel.  The packed RGB24 frame is a flat byte stream: byte at
+// offset a belongs to channel a % 3 and falls in bin (byte >> 4).
+// Block = 384 threads (a multiple of 3 and of 32), so with a grid-stride of gridDim.x*384
+// sixteen-byte vectors every thread sees a constant channel phase: byte b of each of its
+// vectors is channel (phase + b) % 3 -- the three table bases are fixed registers.
+// -------------------------------------------------------------------------------------------
+constexpr int kHistThreads = 384;
+constexpr int kHistWarps = kHistThreads / 32;
+constexpr int kHistSmemWords = kHistWarps * STB_HIST_INTS * 32;  // [warp][bin][lane] u32 = 72 KB
+
+__device__ __forceinline__ void hist_count_word(unsigned wd, unsigned* b0, unsigned* b1, unsigned* b2) {
+  // bytes k = 0..3 of this word use bases (b0,b1,b2,b0): the caller rotates them per word.
+  // Row stride is 32 words (one per lane).
+  atomicAdd(b0 + ((wd >> 4) & 15u) * 32u, 1u);
+  atomicAdd(b1 + ((wd >> 12) & 15u) * 32u, 1u);
+  atomicAdd(b2 + ((wd >> 20) & 15u) * 32u, 1u);
+  atomicAdd(b0 + ((wd >> 28) & 15u) * 32u, 1u);
+}
+
+__device__ __forceinline__ void hist_count_vec(const uint4& q, unsigned* c0, unsigned* c1, unsigned* c2) {
+  // word j starts at byte 4j: channel of its first byte is (phase + 4j) % 3 = (phase + j) % 3
+  hist_count_word(q.x, c0, c1, c2);
+  hist_count_word(q.y, c1, c2, c0);
+  hist_count_word(q.z, c2, c0, c1);
+  hist_count_word(q.w, c0, c1, c2);
+}
+
+template <class Addr>
+__global__ void __launch_bounds__(kHistThreads, 3)
+hist_rgb16_kernel(Addr addr, unsigned long long nbytes, int32_t* __restrict__ out) {
+  STB_DYN_SMEM(unsigned, sh);
+  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  {
+    uint4* z = reinterpret_cast<uint4*>(sh);
+    for (unsigned i = tid; i < kHistSmemWords / 4; i += kHistThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+
+  const uint8_t* f = addr(blockIdx.y);
+  unsigned long long head = (16u - (unsigned)(reinterpret_cast<uintptr_t>(f) & 15u)) & 15u;
+  if (head > nbytes) head = nbytes;
+  const uint4* v = reinterpret_cast<const uint4*>(f + head);
+  const unsigned long long nvec = (nbytes - head) >> 4;
+
+  unsigned* my = sh + warp * (STB_HIST_INTS * 32) + lane;
+  const unsigned gt = blockIdx.x * kHistThreads + tid;
+  const unsigned long long T = (unsigned long long)gridDim.x * kHistThreads;
+  const unsigned ph = (unsigned)((head + gt) % 3u);
+  unsigned* c0 = my + ((ph + 0u) % 3u) * (16 * 32);
+  unsigned* c1 = my + ((ph + 1u) % 3u) * (16 * 32);
+  unsigned* c2 = my + ((ph + 2u) % 3u) * (16 * 32);
+
+  unsigned long long i = gt;
+  for (; i + 3 * T < nvec; i += 4 * T) {
+    const uint4 q0 = __ldg(v + i);
+    const uint4 q1 = __ldg(v + i + T);
+    const uint4 q2 = __ldg(v + i + 2 * T);
+    const uint4 q3 = __ldg(v + i + 3 * T);
+    hist_count_vec(q0, c0, c1, c2);
+    hist_count_vec(q1, c0, c1, c2);
+    hist_count_vec(q2, c0, c1, c2);
+    hist_count_vec(q3, c0, c1, c2);
+  }
+  for (; i < nvec; i += T) {
+    const uint4 q = __ldg(v + i);
+    hist_count_vec(q, c0, c1, c2);
+  }
+  // ragged ends (unaligned base pointer / byte count not a multiple of 16): at most 30 bytes
+  if (blockIdx.x == 0) {
+    const unsigned long long tail0 = head + (nvec << 4);
+    const unsigned long long ntail = nbytes - tail0;
+    if (tid < head + ntail) {
+      const unsigned long long a = tid < head ? tid : tail0 + (tid - head);
+      atomicAdd(my + ((unsigned)(a % 3u) * 16u + (f[a] >> 4)) * 32u, 1u);
+    }
+  }
+  __syncthreads();
+
+  // block reduce: 8 threads per bin, each sums 4 lanes x 12 warps with 16-byte shared loads
+  const unsigned bin = tid >> 3, part = tid & 7u;
+  unsigned s = 0;
+#pragma unroll
+  for (int w = 0; w < kHistWarps; ++w) {
+    const uint4 q = *reinterpret_cast<const uint4*>(sh + (w * STB_HIST_INTS + bin) * 32 + part * 4);
+    s += q.x + q.y + q.z + q.w;
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (part == 0 && s != 0) atomicAdd(out + (size_t)blockIdx.y * STB_HIST_INTS + bin, (int)s);
+}
+
+// -------------------------------------------------------------------------------------------
+// shot scores: S[i] = sum_j max_b |h[i-1][j][b] - h[i][j][b]|
+// one warp per frame: lane l handles bins l and l+32 (48 bins), segmented max over 16 lanes.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+shot_scores_kernel(const int32_t* __restrict__ hist, int n, const int32_t* __restrict__ prev_hist,
+                   int32_t* __restrict__ S) {
+  const int lane = threadIdx.x & 31;
+  const int i = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+  if (i >= n) return;  // whole warp exits together
+  const int32_t* cur = hist + (size_t)i * STB_HIST_INTS;
+  const int32_t* prv = i > 0 ? cur - STB_HIST_INTS : prev_hist;
+  int d0 = 0, d1 = 0;
+  if (prv != nullptr) {
+    d0 = abs(cur[lane] - prv[lane]);                       // channels 0 (lanes 0-15) and 1 (16-31)
+    if (lane < 16) d1 = abs(cur[32 + lane] - prv[32 + lane]);  // channel 2
+  }
+#pragma unroll
+  for (int m = 1; m < 16; m <<= 1) {
+    d0 = max(d0, __shfl_xor_sync(0xffffffffu, d0, m));
+    d1 = max(d1, __shfl_xor_sync(0xffffffffu, d1, m));
+  }
+  const int other = __shfl_sync(0xffffffffu, d0, 16);
+  if (lane == 0) S[i] = d0 + other + d1;
+}
+
+// -------------------------------------------------------------------------------------------
+// FlowHistogram: 64-bin magnitude [0,64) + 64-bin angle [0,360) of an HxWx2 f32 flow field.
+// Arithmetic reproduces OpenCV's cartToPolar (polynomial fastAtan, angleInDegrees) and
+// calcHist's double-precision bin index bit-for-bit.
+// Per-lane private 16-bit counters packed two per word: [warp][64 words][lane].
+// -------------------------------------------------------------------------------------------
+struct PtrAddrF32 {
+  PtrBatch<const float> t;
+  __device__ __forceinline__ const float* operator()(unsigned i) const { return t.p[i]; }
+};
+struct StrideAddrF32 {
+  const float* base;
+  unsigned long long stride;  // bytes
+  __device__ __forceinline__ const float* operator()(unsigned i) const {
+    return reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(base) + (unsigned long long)i * stride);
+  }
+};
+
+constexpr int kFlowHistThreads = 256;
+constexpr int kFlowHistWarps = kFlowHistThreads / 32;
+constexpr int kFlowHistSmemWords = kFlowHistWarps * 64 * 32;  // 64 KB
+constexpr unsigned kFlowHistMaxPxPerThread = 32768;           // 16-bit counters cannot overflow
+
+__device__ __forceinline__ void flow_bins(float x, float y, int& bm, int& ba) {
+  const float m = __fsqrt_rn(__fmaf_rn(x, x, __fmul_rn(y, y)));
+  // magnitude: floor(double(m) * 1.0); floor of a float is exact in float
+  bm = (m < 64.0f) ? __float2int_rd(m) : -1;  // NaN compares false -> dropped, as cvFloor garbage is
+  const float scale = (float)(180.0 / 3.14159265358979323846);
+  const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale,
+              p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float eps = 2.2204460492503131e-16f;  // (float)DBL_EPSILON
+  float a;
+  if (ax >= ay) {
+    const float c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+    const float c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmaf_rn(c2, p7, p5), c2, p3), c2, p1), c);
+  } else {
+    const float c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+    const float c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.0f, __fmul_rn(__fmaf_rn(__fmaf_rn(__fmaf_rn(c2, p7, p5), c2, p3), c2, p1), c));
+  }
+  if (x < 0.0f) a = __fsub_rn(180.0f, a);
+  if (y < 0.0f) a = __fsub_rn(360.0f, a);
+  const double t = __dmul_rn((double)a, 64.0 / 360.0);
+  const int ia = __double2int_rd(t);
+  ba = (ia >= 0 && ia < 64) ? ia : -1;
+}
+
+__device__ __forceinline__ void flow_count(unsigned* my, float x, float y) {
+  int bm, ba;
+  flow_bins(x, y, bm, ba);
+  if (bm >= 0) atomicAdd(my + (bm >> 1) * 32, 1u << ((bm & 1) * 16));
+  if (ba >= 0) atomicAdd(my + (32 + (ba >> 1)) * 32, 1u << ((ba & 1) * 16));
+}
+
+template <class Addr>
+__global__ void __launch_bounds__(kFlowHistThreads, 3)
+flow_hist_kernel(Addr addr, unsigned long long npx, int32_t* __restrict__ out) {
+  STB_DYN_SMEM(unsigned, sh);
+  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  {
+    uint4* z = reinterpret_cast<uint4*>(sh);
+    for (unsigned i = tid; i < kFlowHistSmemWords / 4; i += kFlowHistThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+  const float* f = addr(blockIdx.y);
+  unsigned* my = sh + warp * (64 * 32) + lane;
+  const unsigned long long gt = (unsigned long long)blockIdx.x * kFlowHistThreads + tid;
+  const unsigned long long T = (unsigned long long)gridDim.x * kFlowHistThreads;
+  if ((reinterpret_cast<uintptr_t>(f) & 15u) == 0) {
+    const float4* v = reinterpret_cast<const float4*>(f);
+    const unsigned long long nvec = npx >> 1;
+    unsigned long long i = gt;
+    for (; i + T < nvec; i += 2 * T) {
+      const float4 q0 = __ldg(v + i);
+      const float4 q1 = __ldg(v + i + T);
+      flow_count(my, q0.x, q0.y);
+      flow_count(my, q0.z, q0.w);
+      flow_count(my, q1.x, q1.y);
+      flow_count(my, q1.z, q1.w);
+    }
+    for (; i < nvec; i += T) {
+      const float4 q = __ldg(v + i);
+      flow_count(my, q.x, q.y);
+      flow_count(my, q.z, q.w);
+    }
+    if ((npx & 1ull) && gt == 0) flow_count(my, f[2 * (npx - 1)], f[2 * (npx - 1) + 1]);
+  } else {
+    for (unsigned long long i = gt; i < npx; i += T) flow_count(my, __ldg(f + 2 * i), __ldg(f + 2 * i + 1));
+  }
+  __syncthreads();
+  // reduce: 2 threads per bin, each sums 16 lanes x 8 warps of its 16-bit half
+  const unsigned bin = tid >> 1, part = tid & 1u;
+  const unsigned word = (bin < 64 ? (bin >> 1) : 32 + ((bin - 64) >> 1));
+  const unsigned shift = (bin & 1u) * 16u;
+  unsigned s = 0;
+#pragma unroll
+  for (int w = 0; w < kFlowHistWarps; ++w) {
+    const unsigned* row = sh + (w * 64 + word) * 32 + part * 16;
+#pragma unroll
+    for (int l = 0; l < 16; l += 4) {
+      const uint4 q = *reinterpret_cast<const uint4*>(row + l);
+      s += ((q.x >> shift) & 0xffffu) + ((q.y >> shift) & 0xffffu) + ((q.z >> shift) & 0xffffu) + ((q.w >> shift) & 0xffffu);
+    }
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  if (part == 0 && s != 0) atomicAdd(out + (size_t)blockIdx.y * STB_FLOWHIST_INTS + bin, (int)s);
+}
+
+// -------------------------------------------------------------------------------------------
+// FrameDifference: out = (u8)(cur - prev)
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+frame_diff_kernel(const uint8_t* __restrict__ prev, const uint8_t* __restrict__ cur, uint8_t* __restrict__ out,
+                  unsigned long long n, int vec_ok) {
+  const unsigned long long gt = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long T = (unsigned long long)gridDim.x * blockDim.x;
+  unsigned long long done = 0;
+  if (vec_ok) {
+    const unsigned long long nvec = n >> 4;
+    const uint4* p = reinterpret_cast<const uint4*>(prev);
+    const uint4* c = reinterpret_cast<const uint4*>(cur);
+    uint4* o = reinterpret_cast<uint4*>(out);
+    for (unsigned long long i = gt; i < nvec; i += T) {
+      const uint4 a = __ldg(c + i), b = __ldg(p + i);
+      o[i] = make_uint4(__vsub4(a.x, b.x), __vsub4(a.y, b.y), __vsub4(a.z, b.z), __vsub4(a.w, b.w));
+    }
+    done = nvec << 4;
+  }
+  for (unsigned long long i = done + gt; i < n; i += T) out[i] = (uint8_t)(cur[i] - prev[i]);
+}
+
+// -------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  return dev;
+}
+
+int num_sms() {
+#ifdef STB_CPU_EMU
+  return 2;
+#else
+  static int cached[64] = {};
+  const int dev = current_device();
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached[dev] = n;
+    else return 148;
+  }
+  return cached[dev];
+#endif
+}
+
+template <class Addr>
+static int launch_hist(Addr addr, int n, unsigned long long nbytes, int32_t* d_out, cudaStream_t s) {
+  static bool attr_done[64] = {};  // per device: the attribute is per (function, device)
+  const int dev = current_device();
+  if (!attr_done[dev]) {
+    STB_CUDA(cudaFuncSetAttribute(hist_rgb16_kernel<Addr>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(kHistSmemWords * sizeof(unsigned))));
+    attr_done[dev] = true;
+  }
+  const unsigned long long nvec = nbytes >> 4;
+  // one resident wave (3 blocks/SM) spread over the frames of this launch; never more blocks
+  // than there are 4-vector iterations of work
+  const int wave = num_sms() * 3;
+  long long bpf = (wave + n - 1) / n;
+  const long long max_useful = (long long)((nvec + (unsigned long long)kHistThreads * 4 - 1) / ((unsigned long long)kHistThreads * 4));
+  if (bpf > max_useful) bpf = max_useful;
+  if (bpf < 1) bpf = 1;
+  stb_launch(hist_rgb16_kernel<Addr>, dim3((unsigned)bpf, (unsigned)n), dim3(kHistThreads),
+             kHistSmemWords * sizeof(unsigned), s, addr, nbytes, d_out);
+  STB_CHECK_LAUNCH("hist_rgb16_kernel");
+  return STB_OK;
+}
+
+template <class Addr>
+static int launch_flow_hist(Addr addr, int n, unsigned long long npx, int32_t* d_out, cudaStream_t s) {
+  static bool attr_done[64] = {};
+  const int dev = current_device();
+  if (!attr_done[dev]) {
+    STB_CUDA(cudaFuncSetAttribute(flow_hist_kernel<Addr>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(kFlowHistSmemWords * sizeof(unsigned))));
+    attr_done[dev] = true;
+  }
+  const int wave = num_sms() * 3;
+  long long bpf = (wave + n - 1) / n;
+  const long long max_useful = (long long)((npx / 2 + (unsigned long long)kFlowHistThreads * 2 - 1) / ((unsigned long long)kFlowHistThreads * 2));
+  const long long min_needed = (long long)((npx + (unsigned long long)kFlowHistThreads * kFlowHistMaxPxPerThread - 1) /
+                                           ((unsigned long long)kFlowHistThreads * kFlowHistMaxPxPerThread));
+  if (bpf > max_useful) bpf = max_useful;
+  if (bpf < min_needed) bpf = min_needed;
+  if (bpf < 1) bpf = 1;
+  stb_launch(flow_hist_kernel<Addr>, dim3((unsigned)bpf, (unsigned)n), dim3(kFlowHistThreads),
+             kFlowHistSmemWords * sizeof(unsigned), s, addr, npx, d_out);
+  STB_CHECK_LAUNCH("flow_hist_kernel");
+  return STB_OK;
+}
+
+int flow_hist_device(const float* const* d_flow, int n, unsigned long long npx, int32_t* d_out, cudaStream_t s,
+                     bool zero_out) {
+  if (zero_out) STB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)n * STB_FLOWHIST_INTS * sizeof(int32_t), s));
+  for (int base = 0; base < n; base += kMaxPtrBatch) {
+    const int m = n - base < kMaxPtrBatch ? n - base : kMaxPtrBatch;
+    PtrAddrF32 a;
+    for (int i = 0; i < m; ++i) a.t.p[i] = d_flow[base + i];
+    for (int i = m; i < kMaxPtrBatch; ++i) a.t.p[i] = nullptr;
+    int rc = launch_flow_hist(a, m, npx, d_out + (size_t)base * STB_FLOWHIST_INTS, s);
+    if (rc) return rc;
+  }
+  return STB_OK;
+}
+
+}  // namespace stb
+
+using namespace stb;
+
+extern "C" {
+
+int stb_hist_rgb16(const uint8_t* const* d_frames, int n, int width, int height, int32_t* d_out, stb_stream_t stream) {
+  if (n == 0) return STB_OK;
+  if (!d_frames || !d_out || n < 0 || width <= 0 || height <= 0) {
+    set_error("stb_hist_rgb16: invalid argument (n=%d, %dx%d)", n, width, height);
+    return STB_ERR_INVALID;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned long long nbytes = 3ull * (unsigned long long)width * (unsigned long long)height;
+  STB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)n * STB_HIST_INTS * sizeof(int32_t), s));
+  for (int base = 0; base < n; base += kMaxPtrBatch) {
+    const int m = n - base < kMaxPtrBatch ? n - base : kMaxPtrBatch;
+    PtrAddrU8 a;
+    for (int i = 0; i < m; ++i) {
+      if (!d_frames[base + i]) { set_error("stb_hist_rgb16: frame %d is NULL", base + i); return STB_ERR_INVALID; }
+      a.t.p[i] = d_frames[base + i];
+    }
+    for (int i = m; i < kMaxPtrBatch; ++i) a.t.p[i] = nullptr;
+    int rc = launch_hist(a, m, nbytes, d_out + (size_t)base * STB_HIST_INTS, s);
+    if (rc) return rc;
+  }
+  return STB_OK;
+}
+
+int stb_hist_rgb16_strided(const uint8_t* d_base, size_t stride_bytes, int n, int width, int height, int32_t* d_out,
+                           stb_stream_t stream) {
+  if (n == 0) return STB_OK;
+  const unsigned long long nbytes = 3ull * (unsigned long long)(width > 0 ? width : 0) * (unsigned long long)(height > 0 ? height : 0);
+  if (!d_base || !d_out || n < 0 || width <= 0 || height <= 0 || stride_bytes < nbytes) {
+    set_error("stb_hist_rgb16_strided: invalid argument (n=%d, %dx%d, stride=%zu)", n, width, height, stride_bytes);
+    return STB_ERR_INVALID;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  STB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)n * STB_HIST_INTS * sizeof(int32_t), s));
+  for (int base = 0; base < n; base += 32768) {
+    const int m = n - base < 32768 ? n - base : 32768;
+    StrideAddrU8 a{d_base + (size_t)base * stride_bytes, (unsigned long long)stride_bytes};
+    int rc = launch_hist(a, m, nbytes, d_out + (size_t)base * STB_HIST_INTS, s);
+    if (rc) return rc;
+  }
+  return STB_OK;
+}
+
+int stb_shot_scores(const int32_t* d_hist, int n, const int32_t* d_prev_hist, int32_t* d_S, stb_stream_t stream) {
+  if (n == 0) return STB_OK;
+  if (!d_hist || !d_S || n < 0) {
+    set_error("stb_shot_scores: invalid argument (n=%d)", n);
+    return STB_ERR_INVALID;
+  }
+  const int warps_per_block = 8;
+  stb_launch(shot_scores_kernel, dim3((unsigned)ceil_div(n, warps_per_block)), dim3(warps_per_block * 32), 0,
+             (cudaStream_t)stream, d_hist, n, d_prev_hist, d_S);
+  STB_CHECK_LAUNCH("shot_scores_kernel");
+  return STB_OK;
+}
+
+int stb_flow_hist(const float* const* d_flow, int n, int width, int height, int32_t* d_out, stb_stream_t stream) {
+  if (n == 0) return STB_OK;
+  if (!d_flow || !d_out || n < 0 || width <= 0 || height <= 0) {
+    set_error("stb_flow_hist: invalid argument (n=%d, %dx%d)", n, width, height);
+    return STB_ERR_INVALID;
+  }
+  for (int i = 0; i < n; ++i)
+    if (!d_flow[i]) { set_error("stb_flow_hist: flow %d is NULL", i); return STB_ERR_INVALID; }
+  return flow_hist_device(d_flow, n, (unsigned long long)width * (unsigned long long)height, d_out, (cudaStream_t)stream, true);
+}
+
+int stb_flow_hist_strided(const float* d_base, size_t stride_bytes, int n, int width, int height, int32_t* d_out,
+                          stb_stream_t stream) {
+  if (n == 0) return STB_OK;
+  const unsigned long long npx = (unsigned long long)(width > 0 ? width : 0) * (unsigned long long)(height > 0 ? height : 0);
+  if (!d_base || !d_out || n < 0 || width <= 0 || height <= 0 || stride_bytes < npx * 8 || (stride_bytes & 3)) {
+    set_error("stb_flow_hist_strided: invalid argument (n=%d, %dx%d, stride=%zu)", n, width, height, stride_bytes);
+    return STB_ERR_INVALID;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  STB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)n * STB_FLOWHIST_INTS * sizeof(int32_t), s));
+  for (int base = 0; base < n; base += 32768) {
+    const int m = n - base < 32768 ? n - base : 32768;
+    StrideAddrF32 a{reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(d_base) + (size_t)base * stride_bytes),
+                    (unsigned long long)stride_bytes};
+    int rc = launch_flow_hist(a, m, npx, d_out + (size_t)base * STB_FLOWHIST_INTS, s);
+    if (rc) return rc;
+  }
+  return STB_OK;
+}
+
+int stb_frame_diff(const uint8_t* d_prev, const uint8_t* d_cur, uint8_t* d_out, size_t bytes, stb_stream_t stream) {
+  if (bytes == 0) return STB_OK;
+  if (!d_prev || !d_cur || !d_out) {
+    set_error("stb_frame_diff: NULL pointer");
+    return STB_ERR_INVALID;
+  }
+  const int vec_ok = (((reinterpret_cast<uintptr_t>(d_prev) | reinterpret_cast<uintptr_t>(d_cur) |
+                        reinterpret_cast<uintptr_t>(d_out)) & 15u) == 0) ? 1 : 0;
+  unsigned long long work = vec_ok ? (bytes >> 4) + 15 : bytes;
+  long long blocks = (long long)((work + 255) / 256);
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  stb_launch(frame_diff_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, d_prev, d_cur, d_out,
+             (unsigned long long)bytes, vec_ok);
+  STB_CHECK_LAUNCH("frame_diff_kernel");
+  return STB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+"""Generates the golden fixtures in this directory from the cv2 oracle (oracle/cv2_ops.py),
+i.e. from OpenCV itself -- the library the reference's wrappers call.
+
+Run from the repo root:  python tests/golden/make_golden.py
+Inputs are stored alongside outputs (not only seeds) so the fixtures do not depend on the
+generator's numpy/cv2 versions when they are replayed.
+"""
+import os
+import sys
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), '..', '..'))
+import cv2  # noqa: E402
+from oracle import cv2_ops  # noqa: E402
+from scannertools_b200 import synth  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    meta = dict(cv2=cv2.__version__, numpy=np.__version__)
+
+    # C1: ShotDetection clip -- 1000 frames 640x360, 7 planted cuts, seed 5
+    clip, cuts = synth.cut_clip(5, 1000, 360, 640, n_cuts=7)
+    hists = np.stack([cv2_ops.histogram(f) for f in clip]).astype(np.int32)
+    bounds = cv2_ops.shot_boundaries(list(hists))
+    np.savez_compressed(os.path.join(HERE, 'shot_c1.npz'), hists=hists, boundaries=np.array(bounds, np.int32),
+                        cuts=np.array(cuts, np.int32), scores=cv2_ops.shot_scores(hists),
+                        frame0=clip[0], frame_first_cut=clip[cuts[0]], meta=str(meta))
+    print('shot_c1: boundaries', bounds, 'cuts', cuts)
+
+    # small histogram cases incl. ragged widths (rows not 4/16-byte aligned) and constants
+    hs = {}
+    for name, fr in [('noise_37x53', synth.noise_clip(11, 1, 37, 53)[0]),
+                     ('noise_120x213', synth.noise_clip(12, 1, 120, 213)[0]),
+                     ('const0_64x64', synth.const_clip(0, 1, 64, 64)[0]),
+                     ('const255_64x48', synth.const_clip(255, 1, 48, 64)[0]),
+                     ('one_px', synth.noise_clip(13, 1, 1, 1)[0])]:
+        hs['in_' + name] = fr
+        hs['out_' + name] = cv2_ops.histogram(fr)
+    np.savez_compressed(os.path.join(HERE, 'hist_small.npz'), meta=str(meta), **hs)
+
+    # Farneback: textured pairs at sizes covering 4 scales, 3 scales, and round-half-even
+    fl = {}
+    for name, seed, h, w in [('160x120', 1, 120, 160), ('240x135', 2, 135, 240), ('344x260', 3, 260, 344)]:
+        c = synth.textured_clip(seed, 2, h, w)
+        fl['f0_' + name] = c[0]
+        fl['f1_' + name] = c[1]
+        fl['gray0_' + name] = cv2_ops.gray(c[0])
+        fl['flow_' + name] = cv2_ops.optical_flow(c[0], c[1])
+    np.savez_compressed(os.path.join(HERE, 'flow_small.npz'), meta=str(meta), **fl)
+
+    # FlowHistogram: a real flow field and the stress field
+    fh = {}
+    real = fl['flow_240x135']
+    stress = synth.textured_flow_field(3, 120, 213)
+    for name, f in [('real_240x135', real), ('stress_213x120', stress),
+                    ('stress_33x17', synth.textured_flow_field(4, 17, 33))]:
+        fh['in_' + name] = f
+        fh['out_' + name] = cv2_ops.flow_histogram(f)
+        x, y = cv2.split(f)
+        mag, deg = cv2.cartToPolar(x, y, angleInDegrees=True)
+        if f.size < 4096:
+            fh['mag_' + name] = mag
+            fh['deg_' + name] = deg
+    np.savez_compressed(os.path.join(HERE, 'flowhist.npz'), meta=str(meta), **fh)
+
+    # FrameDifference (intended semantics)
+    a = synth.noise_clip(21, 2, 19, 23)
+    np.savez_compressed(os.path.join(HERE, 'framediff.npz'), prev=a[0], cur=a[1],
+                        out=cv2_ops.frame_difference(a[0], a[1]), meta=str(meta))
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith('.npz'):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == '__main__':
+    main()
