@@ -1,0 +1,53 @@
+"""Builds scannertools_b200/libscannertools_b200.so from csrc/*.cu with nvcc for sm_100a.
+
+In-tree on purpose: the .so is git-ignored but travels with the working tree to the GPU box.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, 'csrc')
+OUT = os.path.join(HERE, 'libscannertools_b200.so')
+OBJ = os.path.join(HERE, 'build')
+SOURCES = ['common.cu', 'hist.cu', 'farneback.cu', 'pipe.cu']
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+              '-Xcompiler', '-fPIC,-fvisibility=hidden', '-I', os.path.join(ROOT, 'include'), '-I', CSRC]
+
+
+def find_nvcc():
+    for c in (os.environ.get('NVCC'), shutil.which('nvcc'), '/usr/local/cuda/bin/nvcc'):
+        if c and os.path.isfile(c):
+            return c
+    raise RuntimeError('nvcc not found: scannertools_b200 has no CPU fallback and cannot be built without CUDA')
+
+
+def _newer(target, deps):
+    if not os.path.isfile(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    nvcc = find_nvcc()
+    os.makedirs(OBJ, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.h', '.cuh'))]
+    headers.append(os.path.join(ROOT, 'include', 'stb.h'))
+    objs = []
+    for s in SOURCES:
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(OBJ, s[:-3] + '.o')
+        objs.append(obj)
+        if force or _newer(obj, [src] + headers):
+            cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+            subprocess.check_call(cmd)
+    if force or _newer(OUT, objs):
+        subprocess.check_call([nvcc, '-shared', '-o', OUT] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a'])
+    return OUT
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -1,0 +1,878 @@
+// Dense Farneback optical flow for sm_100a -- the OpticalFlow op's arithmetic.
+//
+// Replaces cv::cvtColor(BGR2GRAY) + cv::FarnebackOpticalFlow(3, .5, false, 15, 3, 5, 1.2, 0)
+// ::calc as called by scannertools_cpp/imgproc/optical_flow_kernel_cpu.cpp:36-41 (and the
+// cv::cuda variant, optical_flow_kernel_gpu.cpp:66-89).  Algorithm = SURVEY.md Appendix A.
+// This is a from-scratch design, not a port of OpenCV's cudaoptflow:
+//
+//   * planar (SoA) 5-channel polynomial-expansion arrays R and matrix arrays M, so every
+//     global access of a warp is a contiguous run of floats (the CPU code's 5-float
+//     interleaved pixels are hostile to coalescing);
+//   * each pyramid level is produced straight from the full-resolution gray plane by one
+//     kernel (separable Gaussian evaluated only at the columns/rows the bilinear
+//     down-sampler needs), no intermediate full-resolution blurred image exists;
+//   * one fused kernel per displacement-update iteration: 15x15 box sums of the 5 M planes
+//     through shared memory (sliding sums, restarted every 8 outputs) -> 2x2 solve -> new
+//     flow -> bilinear gather of R1 -> next M, so M is read once and written once per
+//     iteration and the flow of inner iterations never touches HBM;
+//   * frames are processed level-major in pair chunks sized so that one chunk's working set
+//     at that level stays resident in the 126 MB L2;
+//   * polynomial expansions are computed once per frame and shared by the two pairs that
+//     contain it (the reference recomputes both pyramids for every pair).
+#include "stb_rt.h"
+
+#include <cmath>
+#include <cstring>
+#include <new>
+
+namespace stb {
+
+constexpr int kMaxScales = 4;     // numLevels = 3 -> up to 4 scales (Appendix A.1)
+constexpr int kMaxGaussTaps = 19; // sigma 3.5 -> ksize 19
+constexpr int kPolyN = 5;
+
+struct PolyConsts {
+  float g[kPolyN + 1], xg[kPolyN + 1], xxg[kPolyN + 1];
+  float ig11, ig03, ig33, ig55;
+};
+
+struct PyrParams {
+  int W, H;          // full resolution
+  int w, h;          // this level
+  int r;             // Gaussian radius (ksize = 2r+1)
+  int max_rows;      // rows of the shared-memory strip
+  double scale_x, scale_y;  // W / w, H / h  (cv::resize's 1/inv_scale)
+  float taps[kMaxGaussTaps];
+};
+
+// ---------------------------------------------------------------------------------------------
+// gray: COLOR_BGR2GRAY fixed point applied to the RGB bytes as they lie in memory
+// (optical_flow_kernel_cpu.cpp:38-39).  16 pixels (48 B in, 16 B out) per
+// thread iteration with 16-byte accesses when the frame base is 16-byte aligned.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned gray_of(unsigned c0, unsigned c1, unsigned c2) {
+  return (c0 * 3735u + c1 * 19235u + c2 * 9798u + (1u << 14)) >> 15;
+}
+
+__global__ void __launch_bounds__(256)
+gray_kernel(PtrBatch<const uint8_t> frames, uint8_t* __restrict__ gray, unsigned long long npx) {
+  const uint8_t* f = frames.p[blockIdx.y];
+  uint8_t* g = gray + (unsigned long long)blockIdx.y * npx;
+  const unsigned long long gt = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long T = (unsigned long long)gridDim.x * blockDim.x;
+  unsigned long long done = 0;
+  if (((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(g)) & 15u) == 0) {
+    const unsigned long long ngroups = npx >> 4;
+    const uint4* v = reinterpret_cast<const uint4*>(f);
+    uint4* o = reinterpret_cast<uint4*>(g);
+    for (unsigned long long i = gt; i < ngroups; i += T) {
+      const uint4 a = __ldg(v + 3 * i), b = __ldg(v + 3 * i + 1), c = __ldg(v + 3 * i + 2);
+      const unsigned wd[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+      unsigned res[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        unsigned packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int px = q * 4 + k;  // pixel within the group; bytes 3px, 3px+1, 3px+2
+          const int b0 = 3 * px, b1 = 3 * px + 1, b2 = 3 * px + 2;
+          const unsigned c0 = (wd[b0 >> 2] >> ((b0 & 3) * 8)) & 0xffu;
+          const unsigned c1 = (wd[b1 >> 2] >> ((b1 & 3) * 8)) & 0xffu;
+          const unsigned c2 = (wd[b2 >> 2] >> ((b2 & 3) * 8)) & 0xffu;
+          packed |= gray_of(c0, c1, c2) << (8 * k);
+        }
+        res[q] = packed;
+      }
+      o[i] = make_uint4(res[0], res[1], res[2], res[3]);
+    }
+    done = ngroups << 4;
+  }
+  for (unsigned long long i = done + gt; i < npx; i += T)
+    g[i] = (uint8_t)gray_of(f[3 * i], f[3 * i + 1], f[3 * i + 2]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pyramid level: I_k = resize_bilinear(GaussianBlur(float(gray), ksize_k, sigma_k), (w_k, h_k))
+// (Appendix A.2).  Tile = 32 x 8 outputs.  Phase 1 evaluates, for every source row the tile
+// needs, the horizontally blurred + horizontally interpolated value at the tile's 32 output
+// columns (REFLECT_101 in x) into shared memory; phase 2 blurs vertically and interpolates in
+// y (REFLECT_101 in y is applied when a row is stored in phase 1).
+// ---------------------------------------------------------------------------------------------
+constexpr int kPyrTW = 32, kPyrTH = 8, kPyrThreads = 256;
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+  // OpenCV BORDER_REFLECT_101; |overshoot| < n for every kernel used here
+  if (n == 1) return 0;
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  if (i < 0) i = -i;
+  return i < n ? i : n - 1;
+}
+
+__device__ __forceinline__ void resize_src(int d, double scale, int n_src, int& s, float& f) {
+  // cv::resize INTER_LINEAR source coordinate for destination index d
+  f = (float)((d + 0.5) * scale - 0.5);
+  s = __float2int_rd(f);
+  f -= (float)s;
+  if (s < 0) { s = 0; f = 0.f; }
+  if (s >= n_src - 1) { s = n_src - 1; f = 0.f; }
+}
+
+__global__ void __launch_bounds__(kPyrThreads)
+pyr_kernel(const uint8_t* __restrict__ gray, float* __restrict__ I, PyrParams p, int frame0) {
+  STB_DYN_SMEM(float, hx);  // [max_rows][32]
+  const int tid = threadIdx.x;
+  const int frame = frame0 + blockIdx.z;
+  const uint8_t* G = gray + (size_t)frame * p.W * p.H;
+  float* out = I + (size_t)frame * p.w * p.h;
+  const int ox0 = blockIdx.x * kPyrTW, oy0 = blockIdx.y * kPyrTH;
+  const int oy_last = min(oy0 + kPyrTH - 1, p.h - 1);
+  int sy_first, sy_last; float fdummy;
+  resize_src(oy0, p.scale_y, p.H, sy_first, fdummy);
+  resize_src(oy_last, p.scale_y, p.H, sy_last, fdummy);
+  const int row_lo = sy_first - p.r;
+  const int nrows = min(sy_last + 1 + p.r - row_lo + 1, p.max_rows);
+
+  // phase 1
+  {
+    const int ox = tid & 31;
+    const int x = ox0 + ox;
+    int sx = 0; float fx = 0.f;
+    if (x < p.w) resize_src(x, p.scale_x, p.W, sx, fx);
+    for (int rr = tid >> 5; rr < nrows; rr += kPyrThreads / 32) {
+      float v = 0.f;
+      if (x < p.w) {
+        const uint8_t* row = G + (size_t)reflect101(row_lo + rr, p.H) * p.W;
+        float a = 0.f, b = 0.f;
+        for (int t = 0; t <= 2 * p.r; ++t) a = fmaf(p.taps[t], (float)row[reflect101(sx + t - p.r, p.W)], a);
+        if (fx != 0.f)
+          for (int t = 0; t <= 2 * p.r; ++t) b = fmaf(p.taps[t], (float)row[reflect101(sx + 1 + t - p.r, p.W)], b);
+        v = a * (1.f - fx) + b * fx;
+      }
+      hx[rr * kPyrTW + ox] = v;
+    }
+  }
+  __syncthreads();
+  // phase 2
+  {
+    const int ox = tid & 31, oy = oy0 + (tid >> 5);
+    const int x = ox0 + ox;
+    if (x < p.w && oy < p.h) {
+      int sy; float fy;
+      resize_src(oy, p.scale_y, p.H, sy, fy);
+      const int base = sy - p.r - row_lo;  // >= 0 by construction
+      float a = 0.f, b = 0.f;
+      for (int t = 0; t <= 2 * p.r; ++t) a = fmaf(p.taps[t], hx[(base + t) * kPyrTW + ox], a);
+      if (fy != 0.f)
+        for (int t = 0; t <= 2 * p.r; ++t) b = fmaf(p.taps[t], hx[(base + 1 + t) * kPyrTW + ox], b);
+      out[(size_t)oy * p.w + x] = a * (1.f - fy) + b * fy;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// polynomial expansion (Appendix A.3): separable 11-tap, replicate borders.  I (h x w) ->
+// R (5 planes of h x w).  Tile 32 x 16, 256 threads, two output rows per thread.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPeTW = 32, kPeTH = 16, kPeThreads = 256;
+constexpr int kPeInW = kPeTW + 2 * kPolyN;  // 42
+constexpr int kPeInH = kPeTH + 2 * kPolyN;  // 26
+
+__global__ void __launch_bounds__(kPeThreads)
+polyexp_kernel(const float* __restrict__ I, float* __restrict__ R, int w, int h, PolyConsts c, int frame0) {
+  __shared__ float in[kPeInH][kPeInW + 1];
+  __shared__ float v0[kPeTH][kPeInW + 1], v1[kPeTH][kPeInW + 1], v2[kPeTH][kPeInW + 1];
+  const int tid = threadIdx.x;
+  const int frame = frame0 + blockIdx.z;
+  const size_t n = (size_t)w * h;
+  const float* src = I + (size_t)frame * n;
+  float* dst = R + (size_t)frame * 5 * n;
+  const int ox0 = blockIdx.x * kPeTW, oy0 = blockIdx.y * kPeTH;
+
+  for (int idx = tid; idx < kPeInH * kPeInW; idx += kPeThreads) {
+    const int yy = idx / kPeInW, xx = idx - yy * kPeInW;
+    const int y = min(max(oy0 + yy - kPolyN, 0), h - 1);
+    const int x = min(max(ox0 + xx - kPolyN, 0), w - 1);
+    in[yy][xx] = __ldg(src + (size_t)y * w + x);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < kPeTH * kPeInW; idx += kPeThreads) {
+    const int ty = idx / kPeInW, xx = idx - ty * kPeInW;
+    const float s0 = in[ty + kPolyN][xx];
+    float r0 = s0 * c.g[0], r1 = 0.f, r2 = 0.f;
+#pragma unroll
+    for (int k = 1; k <= kPolyN; ++k) {
+      const float a = in[ty + kPolyN - k][xx], b = in[ty + kPolyN + k][xx];
+      const float pp = a + b;
+      r0 = fmaf(c.g[k], pp, r0);
+      r1 = fmaf(c.xg[k], b - a, r1);
+      r2 = fmaf(c.xxg[k], pp, r2);
+    }
+    v0[ty][xx] = r0; v1[ty][xx] = r1; v2[ty][xx] = r2;
+  }
+  __syncthreads();
+  const int tx = tid & 31;
+  const int x = ox0 + tx;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int ty = (tid >> 5) + half * 8;
+    const int y = oy0 + ty;
+    if (x >= w || y >= h) continue;
+    const int cx = tx + kPolyN;
+    float b1 = v0[ty][cx] * c.g[0], b2 = 0.f, b3 = v1[ty][cx] * c.g[0], b4 = 0.f, b5 = v2[ty][cx] * c.g[0], b6 = 0.f;
+#pragma unroll
+    for (int k = 1; k <= kPolyN; ++k) {
+      const float p0 = v0[ty][cx + k], m0 = v0[ty][cx - k];
+      const float p1 = v1[ty][cx + k], m1 = v1[ty][cx - k];
+      const float p2 = v2[ty][cx + k], m2 = v2[ty][cx - k];
+      const float tg = p0 + m0;
+      b1 = fmaf(tg, c.g[k], b1);
+      b4 = fmaf(tg, c.xxg[k], b4);
+      b2 = fmaf(p0 - m0, c.xg[k], b2);
+      b3 = fmaf(p1 + m1, c.g[k], b3);
+      b6 = fmaf(p1 - m1, c.xg[k], b6);
+      b5 = fmaf(p2 + m2, c.g[k], b5);
+    }
+    const size_t o = (size_t)y * w + x;
+    dst[o] = b3 * c.ig11;                          // d/dy
+    dst[n + o] = b2 * c.ig11;                      // d/dx
+    dst[2 * n + o] = fmaf(b1, c.ig03, b5 * c.ig33);  // yy
+    dst[3 * n + o] = fmaf(b1, c.ig03, b4 * c.ig33);  // xx
+    dst[4 * n + o] = b6 * c.ig55;                  // xy
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// UpdateMatrices for one pixel (Appendix A.5).  R0, R1: planar 5 x n.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float border_w(int d) { return d < 2 ? 0.14f : 0.4472f; }
+
+__device__ __forceinline__ void update_matrices_px(const float* __restrict__ R0, const float* __restrict__ R1,
+                                                   size_t n, int w, int h, int x, int y, float dx, float dy,
+                                                   float m[5]) {
+  const size_t o = (size_t)y * w + x;
+  float fx = (float)x + dx, fy = (float)y + dy;
+  const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
+  fx -= (float)x1; fy -= (float)y1;
+  float r2, r3, r4, r5, r6;
+  const float q0 = __ldg(R0 + o), q1 = __ldg(R0 + n + o), q2 = __ldg(R0 + 2 * n + o), q3 = __ldg(R0 + 3 * n + o),
+              q4 = __ldg(R0 + 4 * n + o);
+  if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
+    const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+    const float* p = R1 + (size_t)y1 * w + x1;
+#define STB_BILIN(pl) (a00 * __ldg(p + (pl) * n) + a01 * __ldg(p + (pl) * n + 1) + a10 * __ldg(p + (pl) * n + w) + a11 * __ldg(p + (pl) * n + w + 1))
+    r2 = STB_BILIN(0);
+    r3 = STB_BILIN(1);
+    r4 = STB_BILIN(2);
+    r5 = STB_BILIN(3);
+    r6 = STB_BILIN(4);
+#undef STB_BILIN
+    r4 = (q2 + r4) * 0.5f;
+    r5 = (q3 + r5) * 0.5f;
+    r6 = (q4 + r6) * 0.25f;
+  } else {
+    r2 = r3 = 0.f;
+    r4 = q2;
+    r5 = q3;
+    r6 = q4 * 0.5f;
+  }
+  r2 = (q0 - r2) * 0.5f;
+  r3 = (q1 - r3) * 0.5f;
+  r2 += r4 * dy + r6 * dx;
+  r3 += r6 * dy + r5 * dx;
+  if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
+    const float scale = (x < 5 ? border_w(x) : 1.f) * (x >= w - 5 ? border_w(w - x - 1) : 1.f) *
+                        (y < 5 ? border_w(y) : 1.f) * (y >= h - 5 ? border_w(h - y - 1) : 1.f);
+    r2 *= scale; r3 *= scale; r4 *= scale; r5 *= scale; r6 *= scale;
+  }
+  m[0] = r4 * r4 + r6 * r6;
+  m[1] = (r4 + r5) * r6;
+  m[2] = r5 * r5 + r6 * r6;
+  m[3] = r4 * r2 + r6 * r3;
+  m[4] = r6 * r2 + r5 * r3;
+}
+
+// initial M of a level from the up-sampled coarser flow (Appendix A.4-5)
+__global__ void __launch_bounds__(256)
+updmat_init_kernel(const float* __restrict__ R, const float* __restrict__ flow_coarse, float* __restrict__ M,
+                   int w, int h, int wc, int hc, double scale_x, double scale_y, float flow_mul, int pair0) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= w || y >= h) return;
+  const int pair = pair0 + blockIdx.z;
+  const size_t n = (size_t)w * h;
+  float dx = 0.f, dy = 0.f;
+  if (flow_coarse != nullptr) {
+    const float2* fc = reinterpret_cast<const float2*>(flow_coarse) + (size_t)pair * wc * hc;
+    int sx, sy; float fx, fy;
+    resize_src(x, scale_x, wc, sx, fx);
+    resize_src(y, scale_y, hc, sy, fy);
+    const int sx1 = min(sx + 1, wc - 1), sy1 = min(sy + 1, hc - 1);
+    const float2 f00 = __ldg(fc + (size_t)sy * wc + sx), f01 = __ldg(fc + (size_t)sy * wc + sx1);
+    const float2 f10 = __ldg(fc + (size_t)sy1 * wc + sx), f11 = __ldg(fc + (size_t)sy1 * wc + sx1);
+    const float ax0 = 1.f - fx, ay0 = 1.f - fy;
+    const float h0x = f00.x * ax0 + f01.x * fx, h1x = f10.x * ax0 + f11.x * fx;
+    const float h0y = f00.y * ax0 + f01.y * fx, h1y = f10.y * ax0 + f11.y * fx;
+    dx = (h0x * ay0 + h1x * fy) * flow_mul;
+    dy = (h0y * ay0 + h1y * fy) * flow_mul;
+  }
+  float m[5];
+  update_matrices_px(R + (size_t)pair * 5 * n, R + (size_t)(pair + 1) * 5 * n, n, w, h, x, y, dx, dy, m);
+  float* Mo = M + (size_t)pair * 5 * n + (size_t)y * w + x;
+#pragma unroll
+  for (int c = 0; c < 5; ++c) Mo[c * n] = m[c];
+}
+
+// ---------------------------------------------------------------------------------------------
+// one displacement-update iteration (Appendix A.6), fused:
+//   box sums (2m+1)^2 of the 5 planes of M (replicate border) -> 2x2 solve -> flow
+//   -> (UPDATE)  UpdateMatrices with the new flow -> M_out
+//   -> (!UPDATE) flow written out (float2 per pixel, interleaved dx,dy -- the op's layout)
+// Tile 64 x 32, 256 threads.  Per plane: raw tile (+halo) -> shared; vertical sliding sums
+// (restart every 8 rows) -> transposed shared array; horizontal sliding sums by
+// (lane = row, warp = 8-column group) into registers.  After the solve, flow goes through
+// shared memory so the global-memory phase runs with lanes along x (coalesced).
+// ---------------------------------------------------------------------------------------------
+constexpr int kItTW = 64, kItTH = 32, kItThreads = 256;
+constexpr int kItMaxHalo = 15;  // win_size <= 31
+
+template <bool UPDATE>
+__global__ void __launch_bounds__(kItThreads, 2)
+iter_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const float* __restrict__ R,
+            PtrBatch<float> flow_out, int w, int h, int m, int pair0) {
+  STB_DYN_SMEM(float, sm);
+  const int rawW = kItTW + 2 * m, rawH = kItTH + 2 * m;
+  const int rawS = rawW + 2;              // row stride of raw
+  float* raw = sm;                        // [rawH][rawS]
+  float* Vt = sm + rawH * rawS;           // [rawW][33]   (transposed vertical sums)
+  float2* fl = reinterpret_cast<float2*>(sm);  // [32][64] aliases raw/Vt after the box phase
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pair = pair0 + blockIdx.z;
+  const size_t n = (size_t)w * h;
+  const float* Mp = Min + (size_t)pair * 5 * n;
+  const int ox0 = blockIdx.x * kItTW, oy0 = blockIdx.y * kItTH;
+  const int win = 2 * m + 1;
+
+  float sums[5][8];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    const float* plane = Mp + (size_t)c * n;
+    for (int idx = tid; idx < rawH * rawW; idx += kItThreads) {
+      const int yy = idx / rawW, xx = idx - yy * rawW;
+      const int y = min(max(oy0 + yy - m, 0), h - 1);
+      const int x = min(max(ox0 + xx - m, 0), w - 1);
+      raw[yy * rawS + xx] = __ldg(plane + (size_t)y * w + x);
+    }
+    __syncthreads();
+    // vertical: item = (column cx, row group g of 8 output rows)
+    for (int item = tid; item < rawW * 4; item += kItThreads) {
+      const int g = item / rawW, cx = item - g * rawW;
+      const float* col = raw + (g * 8) * rawS + cx;
+      float s = 0.f;
+      for (int j = 0; j < win; ++j) s += col[j * rawS];
+      Vt[cx * 33 + g * 8] = s;
+#pragma unroll
+      for (int i = 1; i < 8; ++i) {
+        s += col[(i + win - 1) * rawS] - col[(i - 1) * rawS];
+        Vt[cx * 33 + g * 8 + i] = s;
+      }
+    }
+    __syncthreads();
+    // horizontal: lane = output row, warp = group of 8 output columns
+    {
+      const float* rowp = Vt + (warp * 8) * 33 + lane;
+      float s = 0.f;
+      for (int j = 0; j < win; ++j) s += rowp[j * 33];
+      sums[c][0] = s;
+#pragma unroll
+      for (int i = 1; i < 8; ++i) {
+        s += rowp[(i + win - 1) * 33] - rowp[(i - 1) * 33];
+        sums[c][i] = s;
+      }
+    }
+    // the next plane's raw load may start now (raw was last read before the previous barrier);
+    // its vertical pass only starts after the barrier that follows that load, i.e. after every
+    // thread finished reading Vt above.
+  }
+  __syncthreads();  // all reads of raw/Vt done before fl (aliased) is written
+
+  const float inv_area = 1.f / (float)(win * win);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float g11 = sums[0][i] * inv_area, g12 = sums[1][i] * inv_area, g22 = sums[2][i] * inv_area;
+    const float h1 = sums[3][i] * inv_area, h2 = sums[4][i] * inv_area;
+    // differences of products with the rounding error of one product recovered by FMA
+    const float w12 = g12 * g12;
+    const float det = fmaf(g11, g22, -w12) + fmaf(-g12, g12, w12);
+    const float idet = 1.f / (det + 1e-3f);
+    const float t1 = g12 * h1;
+    const float nx = fmaf(g11, h2, -t1) + fmaf(-g12, h1, t1);
+    const float t2 = g12 * h2;
+    const float ny = fmaf(g22, h1, -t2) + fmaf(-g12, h2, t2);
+    fl[lane * kItTW + warp * 8 + i] = make_float2(nx * idet, ny * idet);
+  }
+  __syncthreads();
+
+  // global phase: lanes along x
+  const int tx = tid & 63;
+  const int x = ox0 + tx;
+  if (x < w) {
+#pragma unroll 2
+    for (int i = 0; i < 8; ++i) {
+      const int ty = (tid >> 6) + 4 * i;
+      const int y = oy0 + ty;
+      if (y >= h) break;
+      const float2 f = fl[ty * kItTW + tx];
+      if (UPDATE) {
+        float mm[5];
+        update_matrices_px(R + (size_t)pair * 5 * n, R + (size_t)(pair + 1) * 5 * n, n, w, h, x, y, f.x, f.y, mm);
+        float* Mo = Mout + (size_t)pair * 5 * n + (size_t)y * w + x;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) Mo[c * n] = mm[c];
+      } else {
+        reinterpret_cast<float2*>(flow_out.p[blockIdx.z])[(size_t)y * w + x] = f;
+      }
+    }
+  }
+}
+
+static inline size_t iter_smem_bytes(int m) {
+  const int rawW = kItTW + 2 * m, rawH = kItTH + 2 * m;
+  size_t box = ((size_t)rawH * (rawW + 2) + (size_t)rawW * 33) * sizeof(float);
+  size_t fl = (size_t)kItTW * kItTH * sizeof(float2);
+  return box > fl ? box : fl;
+}
+
+}  // namespace stb
+
+// =============================================================================================
+// host side: handle, workspace, level-major chunked schedule
+// =============================================================================================
+using namespace stb;
+
+struct stb_farneback {
+  int W, H, max_pairs, device;
+  stb_farneback_params prm;
+  int nscales;
+  int w[8], h[8];
+  PolyConsts pc;
+  PyrParams pyr[kMaxScales];
+  int chunk[kMaxScales];
+  // device workspace
+  uint8_t* gray;    // [F][H*W]
+  float* I;         // [F][N_k]      (N_0 sized)
+  float* R;         // [F][5][N_k]   (N_0 sized)
+  float* M[2];      // [P][5][N_k]   (N_0 sized)
+  float* flow[2];   // [P][N_k*2]    level >= 1 only (N_1 sized)
+  float* flow0;     // [P][N_0*2]    lazily allocated: level-0 flow when the caller wants only histograms
+  size_t bytes;
+  // debug taps
+  int dbg_level, dbg_pair;
+  float *dbg_I0, *dbg_I1, *dbg_R0, *dbg_R1, *dbg_M0, *dbg_flow;
+};
+
+namespace stb {
+
+static int cv_round_d(double v) { return (int)std::nearbyint(v); }
+
+static void gaussian_taps(int ksize, double sigma, float* taps) {
+  // cv::getGaussianKernel(ksize, sigma, CV_32F)
+  if (ksize == 3 && sigma <= 0) { taps[0] = 0.25f; taps[1] = 0.5f; taps[2] = 0.25f; return; }
+  if (sigma <= 0) sigma = 0.3 * ((ksize - 1) * 0.5 - 1) + 0.8;
+  double t[kMaxGaussTaps], sum = 0;
+  for (int i = 0; i < ksize; ++i) {
+    const double x = i - (ksize - 1) * 0.5;
+    t[i] = std::exp(-0.5 / (sigma * sigma) * x * x);
+    sum += t[i];
+  }
+  for (int i = 0; i < ksize; ++i) taps[i] = (float)(t[i] / sum);
+}
+
+static bool invert_spd6(double A[6][6], double inv[6][6]) {
+  // Cholesky A = L L^T, then solve for the identity columns
+  double L[6][6] = {};
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double s = A[i][j];
+      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+      if (i == j) { if (s <= 0) return false; L[i][i] = std::sqrt(s); }
+      else L[i][j] = s / L[j][j];
+    }
+  for (int c = 0; c < 6; ++c) {
+    double y[6], x[6];
+    for (int i = 0; i < 6; ++i) {
+      double s = (i == c) ? 1.0 : 0.0;
+      for (int k = 0; k < i; ++k) s -= L[i][k] * y[k];
+      y[i] = s / L[i][i];
+    }
+    for (int i = 5; i >= 0; --i) {
+      double s = y[i];
+      for (int k = i + 1; k < 6; ++k) s -= L[k][i] * x[k];
+      x[i] = s / L[i][i];
+    }
+    for (int i = 0; i < 6; ++i) inv[i][c] = x[i];
+  }
+  return true;
+}
+
+static bool poly_consts(int n, double sigma, PolyConsts* pc) {
+  // FarnebackPrepareGaussian (Appendix A.3)
+  float gf[2 * kPolyN + 1];
+  if (sigma < 1.1920929e-07) sigma = n * 0.3;
+  double s = 0;
+  for (int x = -n; x <= n; ++x) { gf[x + n] = (float)std::exp(-x * x / (2 * sigma * sigma)); s += gf[x + n]; }
+  s = 1. / s;
+  for (int x = -n; x <= n; ++x) gf[x + n] = (float)(gf[x + n] * s);
+  for (int x = 0; x <= n; ++x) {
+    pc->g[x] = gf[x + n];
+    pc->xg[x] = (float)(x * gf[x + n]);
+    pc->xxg[x] = (float)(x * x * gf[x + n]);
+  }
+  double G[6][6] = {}, inv[6][6];
+  for (int y = -n; y <= n; ++y)
+    for (int x = -n; x <= n; ++x) {
+      const float gg = gf[y + n] * gf[x + n];  // float products, accumulated in double, as OpenCV does
+      G[0][0] += gg;
+      G[1][1] += gg * x * x;
+      G[3][3] += gg * x * x * x * x;
+      G[5][5] += gg * x * x * y * y;
+    }
+  G[2][2] = G[0][3] = G[0][4] = G[3][0] = G[4][0] = G[1][1];
+  G[4][4] = G[3][3];
+  G[3][4] = G[4][3] = G[5][5];
+  if (!invert_spd6(G, inv)) return false;
+  pc->ig11 = (float)inv[1][1]; pc->ig03 = (float)inv[0][3]; pc->ig33 = (float)inv[3][3]; pc->ig55 = (float)inv[5][5];
+  return true;
+}
+
+static int validate_params(const stb_farneback_params& p) {
+  if (p.num_levels < 0 || p.num_levels > kMaxScales - 1 || p.pyr_scale != 0.5 || p.fast_pyramids != 0 ||
+      p.win_size < 3 || (p.win_size & 1) == 0 || p.win_size > 2 * kItMaxHalo + 1 || p.num_iters < 1 ||
+      p.poly_n != kPolyN || p.flags != 0) {
+    set_error("stb_farneback: unsupported parameters (levels=%d pyr_scale=%g fast=%d win=%d iters=%d poly_n=%d flags=%d)",
+              p.num_levels, p.pyr_scale, p.fast_pyramids, p.win_size, p.num_iters, p.poly_n, p.flags);
+    return STB_ERR_UNSUPPORTED;
+  }
+  return STB_OK;
+}
+
+static int plan_levels(int W, int H, const stb_farneback_params& p, int* ws, int* hs) {
+  // Appendix A.1
+  int k; double scale = 1;
+  for (k = 0; k < p.num_levels; ++k) {
+    scale *= p.pyr_scale;
+    if (W * scale < 32 || H * scale < 32) break;
+  }
+  const int levels = k;
+  for (k = 0; k <= levels; ++k) {
+    double sc = 1;
+    for (int i = 0; i < k; ++i) sc *= p.pyr_scale;
+    ws[k] = cv_round_d(W * sc);
+    hs[k] = cv_round_d(H * sc);
+  }
+  return levels + 1;
+}
+
+struct WsLayout { size_t gray, I, R, M, flow, total; };
+
+static WsLayout ws_layout(int W, int H, int P, int nscales, const int* ws, const int* hs) {
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t F = (size_t)P + 1, N0 = (size_t)W * H;
+  const size_t N1 = nscales > 1 ? (size_t)ws[1] * hs[1] : 0;
+  WsLayout l;
+  l.gray = al(F * N0);
+  l.I = al(F * N0 * sizeof(float));
+  l.R = al(F * 5 * N0 * sizeof(float));
+  l.M = al((size_t)P * 5 * N0 * sizeof(float));
+  l.flow = al((size_t)P * N1 * 2 * sizeof(float));
+  l.total = l.gray + l.I + l.R + 2 * l.M + 2 * l.flow;
+  return l;
+}
+
+}  // namespace stb
+
+extern "C" {
+
+void stb_farneback_default_params(stb_farneback_params* p) {
+  if (!p) return;
+  p->num_levels = 3; p->pyr_scale = 0.5; p->fast_pyramids = 0; p->win_size = 15;
+  p->num_iters = 3; p->poly_n = 5; p->poly_sigma = 1.2; p->flags = 0;
+}
+
+size_t stb_farneback_workspace_bytes(int width, int height, int max_pairs, const stb_farneback_params* params) {
+  stb_farneback_params p;
+  if (params) p = *params; else stb_farneback_default_params(&p);
+  if (width <= 0 || height <= 0 || max_pairs <= 0 || validate_params(p) != STB_OK) return 0;
+  int ws[8], hs[8];
+  const int ns = plan_levels(width, height, p, ws, hs);
+  return ws_layout(width, height, max_pairs, ns, ws, hs).total;
+}
+
+int stb_farneback_create(int width, int height, int max_pairs, const stb_farneback_params* params, stb_farneback** out) {
+  if (!out) { set_error("stb_farneback_create: out is NULL"); return STB_ERR_INVALID; }
+  *out = nullptr;
+  stb_farneback_params p;
+  if (params) p = *params; else stb_farneback_default_params(&p);
+  if (width <= 0 || height <= 0 || max_pairs <= 0 || (long long)width * height > (1ll << 28)) {
+    set_error("stb_farneback_create: invalid geometry %dx%d, max_pairs=%d", width, height, max_pairs);
+    return STB_ERR_INVALID;
+  }
+  int rc = validate_params(p);
+  if (rc) return rc;
+  stb_farneback* h = new (std::nothrow) stb_farneback();
+  if (!h) { set_error("stb_farneback_create: out of host memory"); return STB_ERR_ALLOC; }
+  std::memset(h, 0, sizeof(*h));
+  h->W = width; h->H = height; h->max_pairs = max_pairs; h->prm = p; h->dbg_level = -1;
+  h->device = current_device();
+  h->nscales = plan_levels(width, height, p, h->w, h->h);
+  if (!poly_consts(p.poly_n, p.poly_sigma, &h->pc)) {
+    delete h;
+    set_error("stb_farneback_create: singular polynomial basis (poly_sigma=%g)", p.poly_sigma);
+    return STB_ERR_INVALID;
+  }
+  for (int k = 0; k < h->nscales; ++k) {
+    PyrParams& q = h->pyr[k];
+    double scale = 1;
+    for (int i = 0; i < k; ++i) scale *= p.pyr_scale;
+    const double sigma = (1. / scale - 1) * 0.5;
+    int ksize = cv_round_d(sigma * 5) | 1;
+    if (ksize < 3) ksize = 3;
+    q.W = width; q.H = height; q.w = h->w[k]; q.h = h->h[k]; q.r = ksize / 2;
+    q.scale_x = 1. / ((double)q.w / width);
+    q.scale_y = 1. / ((double)q.h / height);
+    gaussian_taps(ksize, sigma, q.taps);
+    q.max_rows = (int)std::ceil((kPyrTH - 1) * q.scale_y) + 3 + 2 * q.r;
+    // pair chunk whose level-k working set (R0,R1 shared + M,M' + I + flow ~ 23 floats/px) fits in ~half of L2
+    const double per_pair = 23.0 * 4.0 * (double)q.w * q.h;
+    int c = (int)(64.0 * 1024 * 1024 / per_pair);
+    if (c < 1) c = 1;
+    if (c > kMaxPtrBatch) c = kMaxPtrBatch;
+    h->chunk[k] = c;
+  }
+  const WsLayout l = ws_layout(width, height, max_pairs, h->nscales, h->w, h->h);
+  uint8_t* base = nullptr;
+  cudaError_t e = cudaMalloc((void**)&base, l.total);
+  if (e != cudaSuccess) {
+    delete h;
+    (void)cudaGetLastError();
+    set_error("stb_farneback_create: cudaMalloc(%zu bytes) failed: %s", l.total, cudaGetErrorString(e));
+    return (int)e == 100 || (int)e == 35 ? STB_ERR_NO_DEVICE : STB_ERR_ALLOC;
+  }
+  h->bytes = l.total;
+  size_t off = 0;
+  h->gray = base; off += l.gray;
+  h->I = (float*)(base + off); off += l.I;
+  h->R = (float*)(base + off); off += l.R;
+  h->M[0] = (float*)(base + off); off += l.M;
+  h->M[1] = (float*)(base + off); off += l.M;
+  h->flow[0] = (float*)(base + off); off += l.flow;
+  h->flow[1] = (float*)(base + off); off += l.flow;
+#ifndef STB_CPU_EMU
+  e = cudaFuncSetAttribute(iter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iter_smem_bytes(kItMaxHalo));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(iter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iter_smem_bytes(kItMaxHalo));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(pyr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  if (e != cudaSuccess) {
+    cudaFree(base);
+    delete h;
+    return cuda_fail(e, "cudaFuncSetAttribute");
+  }
+#endif
+  *out = h;
+  return STB_OK;
+}
+
+int stb_farneback_destroy(stb_farneback* h) {
+  if (!h) return STB_OK;
+  if (h->gray) cudaFree(h->gray);
+  if (h->flow0) cudaFree(h->flow0);
+  delete h;
+  return STB_OK;
+}
+
+int stb_farneback_levels(const stb_farneback* h, int* widths, int* heights) {
+  if (!h) return 0;
+  for (int k = 0; k < h->nscales; ++k) {
+    if (widths) widths[k] = h->w[k];
+    if (heights) heights[k] = h->h[k];
+  }
+  return h->nscales;
+}
+
+int stb_farneback_debug_set(stb_farneback* h, int level, int pair, float* d_I0, float* d_I1, float* d_R0, float* d_R1,
+                            float* d_M0, float* d_flow_level) {
+  if (!h) { set_error("stb_farneback_debug_set: NULL handle"); return STB_ERR_INVALID; }
+  h->dbg_level = level; h->dbg_pair = pair;
+  h->dbg_I0 = d_I0; h->dbg_I1 = d_I1; h->dbg_R0 = d_R0; h->dbg_R1 = d_R1; h->dbg_M0 = d_M0; h->dbg_flow = d_flow_level;
+  return STB_OK;
+}
+
+}  // extern "C"
+
+namespace stb {
+
+static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_t s) {
+  const int F = n + 1;
+  const int m = h->prm.win_size / 2;
+  const size_t it_smem = iter_smem_bytes(m);
+  int fl_cur = 0;  // h->flow[fl_cur] receives this level's flow (levels >= 1)
+  for (int k = h->nscales - 1; k >= 0; --k) {
+    const int w = h->w[k], hh = h->h[k];
+    const size_t nk = (size_t)w * hh;
+    const PyrParams& pp = h->pyr[k];
+    const float* coarse = (k == h->nscales - 1) ? nullptr : h->flow[fl_cur ^ 1];
+    const int wc = coarse ? h->w[k + 1] : 0, hc = coarse ? h->h[k + 1] : 0;
+    const double up_sx = coarse ? 1. / ((double)w / wc) : 0, up_sy = coarse ? 1. / ((double)hh / hc) : 0;
+    int frames_done = 0;
+    const bool dbg = (h->dbg_level == k);
+    for (int p0 = 0; p0 < n; p0 += h->chunk[k]) {
+      const int p1 = (p0 + h->chunk[k] < n) ? p0 + h->chunk[k] : n;
+      const int np = p1 - p0;
+      // frames [fa, fb) still need I_k and R_k
+      const int fa = frames_done, fb = p1 + 1;
+      if (fb > fa) {
+        const size_t pyr_smem = (size_t)pp.max_rows * kPyrTW * sizeof(float);
+        stb_launch(pyr_kernel, dim3(ceil_div(w, kPyrTW), ceil_div(hh, kPyrTH), fb - fa), dim3(kPyrThreads), pyr_smem, s,
+                   (const uint8_t*)h->gray, h->I, pp, fa);
+        STB_CHECK_LAUNCH("pyr_kernel");
+        stb_launch(polyexp_kernel, dim3(ceil_div(w, kPeTW), ceil_div(hh, kPeTH), fb - fa), dim3(kPeThreads), 0, s,
+                   (const float*)h->I, h->R, w, hh, h->pc, fa);
+        STB_CHECK_LAUNCH("polyexp_kernel");
+        frames_done = fb;
+      }
+      (void)F;
+      stb_launch(updmat_init_kernel, dim3(ceil_div(w, 32), ceil_div(hh, 8), np), dim3(256), 0, s, (const float*)h->R,
+                 coarse, h->M[0], w, hh, wc, hc, up_sx, up_sy, (float)(1. / h->prm.pyr_scale), p0);
+      STB_CHECK_LAUNCH("updmat_init_kernel");
+      if (dbg && h->dbg_pair >= p0 && h->dbg_pair < p1) {
+        const int dp = h->dbg_pair;
+        if (h->dbg_I0) STB_CUDA(cudaMemcpyAsync(h->dbg_I0, h->I + (size_t)dp * nk, nk * 4, cudaMemcpyDeviceToDevice, s));
+        if (h->dbg_I1) STB_CUDA(cudaMemcpyAsync(h->dbg_I1, h->I + (size_t)(dp + 1) * nk, nk * 4, cudaMemcpyDeviceToDevice, s));
+        if (h->dbg_R0) STB_CUDA(cudaMemcpyAsync(h->dbg_R0, h->R + (size_t)dp * 5 * nk, nk * 20, cudaMemcpyDeviceToDevice, s));
+        if (h->dbg_R1) STB_CUDA(cudaMemcpyAsync(h->dbg_R1, h->R + (size_t)(dp + 1) * 5 * nk, nk * 20, cudaMemcpyDeviceToDevice, s));
+        if (h->dbg_M0) STB_CUDA(cudaMemcpyAsync(h->dbg_M0, h->M[0] + (size_t)dp * 5 * nk, nk * 20, cudaMemcpyDeviceToDevice, s));
+      }
+      PtrBatch<float> fo;
+      for (int i = 0; i < kMaxPtrBatch; ++i) fo.p[i] = nullptr;
+      for (int i = 0; i < np; ++i)
+        fo.p[i] = (k == 0) ? d_flow[p0 + i] : h->flow[fl_cur] + (size_t)(p0 + i) * nk * 2;
+      int mc = 0;
+      const dim3 grid(ceil_div(w, kItTW), ceil_div(hh, kItTH), np);
+      for (int it = 0; it < h->prm.num_iters; ++it) {
+        if (it < h->prm.num_iters - 1) {
+          stb_launch(iter_kernel<true>, grid, dim3(kItThreads), it_smem, s, (const float*)h->M[mc], h->M[mc ^ 1],
+                     (const float*)h->R, fo, w, hh, m, p0);
+          mc ^= 1;
+        } else {
+          stb_launch(iter_kernel<false>, grid, dim3(kItThreads), it_smem, s, (const float*)h->M[mc], (float*)nullptr,
+                     (const float*)h->R, fo, w, hh, m, p0);
+        }
+        STB_CHECK_LAUNCH("iter_kernel");
+      }
+      if (dbg && h->dbg_flow && h->dbg_pair >= p0 && h->dbg_pair < p1)
+        STB_CUDA(cudaMemcpyAsync(h->dbg_flow, fo.p[h->dbg_pair - p0], nk * 8, cudaMemcpyDeviceToDevice, s));
+    }
+    fl_cur ^= 1;
+  }
+  return STB_OK;
+}
+
+static int check_run_args(stb_farneback* h, const void* frames, int n, const char* who) {
+  if (!h || !frames || n < 0) { set_error("%s: invalid argument", who); return STB_ERR_INVALID; }
+  if (n > h->max_pairs) { set_error("%s: n=%d exceeds max_pairs=%d", who, n, h->max_pairs); return STB_ERR_INVALID; }
+  return STB_OK;
+}
+
+static int ensure_flow0(stb_farneback* h) {
+  if (h->flow0) return STB_OK;
+  cudaError_t e = cudaMalloc((void**)&h->flow0, (size_t)h->max_pairs * h->W * h->H * 2 * sizeof(float));
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("stb_farneback: cudaMalloc of the internal flow buffer failed: %s", cudaGetErrorString(e));
+    return STB_ERR_ALLOC;
+  }
+  return STB_OK;
+}
+
+static int to_gray(stb_farneback* h, const uint8_t* const* d_rgb, int F, cudaStream_t s) {
+  const unsigned long long npx = (unsigned long long)h->W * h->H;
+  long long blocks = (long long)((npx / 16 + 255) / 256);
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  for (int base = 0; base < F; base += kMaxPtrBatch) {
+    const int mcount = F - base < kMaxPtrBatch ? F - base : kMaxPtrBatch;
+    PtrBatch<const uint8_t> t;
+    for (int i = 0; i < kMaxPtrBatch; ++i) t.p[i] = nullptr;
+    for (int i = 0; i < mcount; ++i) {
+      if (!d_rgb[base + i]) { set_error("stb_farneback_run: frame %d is NULL", base + i); return STB_ERR_INVALID; }
+      t.p[i] = d_rgb[base + i];
+    }
+    stb_launch(gray_kernel, dim3((unsigned)blocks, (unsigned)mcount), dim3(256), 0, s, t, h->gray + (size_t)base * npx, npx);
+    STB_CHECK_LAUNCH("gray_kernel");
+  }
+  return STB_OK;
+}
+
+}  // namespace stb
+
+extern "C" {
+
+int stb_farneback_run(stb_farneback* h, const uint8_t* const* d_rgb, int n, float* const* d_flow, stb_stream_t stream) {
+  int rc = check_run_args(h, d_rgb, n, "stb_farneback_run");
+  if (rc) return rc;
+  if (n == 0) return STB_OK;
+  if (!d_flow) { set_error("stb_farneback_run: d_flow is NULL"); return STB_ERR_INVALID; }
+  for (int i = 0; i < n; ++i)
+    if (!d_flow[i]) { set_error("stb_farneback_run: d_flow[%d] is NULL", i); return STB_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  rc = to_gray(h, d_rgb, n + 1, s);
+  if (rc) return rc;
+  return run_levels(h, n, d_flow, s);
+}
+
+int stb_farneback_run_gray(stb_farneback* h, const uint8_t* const* d_gray, int n, float* const* d_flow, stb_stream_t stream) {
+  int rc = check_run_args(h, d_gray, n, "stb_farneback_run_gray");
+  if (rc) return rc;
+  if (n == 0) return STB_OK;
+  if (!d_flow) { set_error("stb_farneback_run_gray: d_flow is NULL"); return STB_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t npx = (size_t)h->W * h->H;
+  for (int i = 0; i <= n; ++i) {
+    if (!d_gray[i] || (i < n && !d_flow[i])) { set_error("stb_farneback_run_gray: NULL pointer at %d", i); return STB_ERR_INVALID; }
+    STB_CUDA(cudaMemcpyAsync(h->gray + (size_t)i * npx, d_gray[i], npx, cudaMemcpyDeviceToDevice, s));
+  }
+  return run_levels(h, n, d_flow, s);
+}
+
+int stb_farneback_run_hist(stb_farneback* h, const uint8_t* const* d_rgb, int n, float* const* d_flow,
+                           int32_t* d_flow_hist, stb_stream_t stream) {
+  int rc = check_run_args(h, d_rgb, n, "stb_farneback_run_hist");
+  if (rc) return rc;
+  if (n == 0) return STB_OK;
+  if (!d_flow_hist) { set_error("stb_farneback_run_hist: d_flow_hist is NULL"); return STB_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  float* tmp[kMaxPtrBatch * 4];
+  float** fl = nullptr;
+  float** heap = nullptr;
+  if (d_flow) {
+    for (int i = 0; i < n; ++i)
+      if (!d_flow[i]) { set_error("stb_farneback_run_hist: d_flow[%d] is NULL", i); return STB_ERR_INVALID; }
+    fl = const_cast<float**>(d_flow);
+  } else {
+    rc = ensure_flow0(h);
+    if (rc) return rc;
+    if (n <= kMaxPtrBatch * 4) fl = tmp;
+    else { heap = new (std::nothrow) float*[n]; if (!heap) { set_error("out of host memory"); return STB_ERR_ALLOC; } fl = heap; }
+    for (int i = 0; i < n; ++i) fl[i] = h->flow0 + (size_t)i * h->W * h->H * 2;
+  }
+  rc = to_gray(h, d_rgb, n + 1, s);
+  if (!rc) rc = run_levels(h, n, fl, s);
+  if (!rc) rc = flow_hist_device(fl, n, (unsigned long long)h->W * h->H, d_flow_hist, s, true);
+  delete[] heap;
+  return rc;
+}
+
+}  // extern "C"

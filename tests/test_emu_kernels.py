@@ -1,0 +1,109 @@
+"""Kernel-LOGIC tests without a GPU: the product's .cu sources are compiled with g++ against
+tests/cuda_emu (a CPU emulation of blocks/threads/shared memory/warp collectives) and checked
+against the oracle.  This exercises indexing, halos, tiling and the host-side level schedule;
+it says nothing about performance and is not a product path (see cuda_emu.h)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, epe
+from oracle import restate
+from scannertools_b200 import _lib, synth
+
+sys.path.insert(0, os.path.join(ROOT, 'tests', 'cuda_emu'))
+
+
+@pytest.fixture(scope='module')
+def emu():
+    import build_emu
+    return _lib.bind(C.CDLL(build_emu.build()))
+
+
+def P(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def test_emu_histogram_ragged_and_unaligned(emu):
+    for (h, w) in [(37, 53), (1, 1), (64, 64)]:
+        fr = synth.noise_clip(1, 2, h, w)
+        out = np.full((2, 48), -1, np.int32)
+        assert emu.stb_hist_rgb16(_lib.ptr_table([f.ctypes.data for f in fr]), 2, w, h, P(out), None) == 0
+        ref = np.stack([restate.histogram(f).reshape(-1) for f in fr])
+        assert np.array_equal(out, ref)
+        buf = np.zeros(fr[0].size + 32, np.uint8)
+        for off in (1, 7):
+            buf[off:off + fr[0].size] = fr[0].reshape(-1)
+            o1 = np.zeros(48, np.int32)
+            assert emu.stb_hist_rgb16_strided(C.c_void_p(buf.ctypes.data + off), fr[0].size, 1, w, h, P(o1), None) == 0
+            assert np.array_equal(o1, ref[0])
+    assert emu.stb_hist_rgb16(None, 0, 4, 4, None, None) == 0          # empty batch is a no-op
+    assert emu.stb_hist_rgb16(None, 2, 4, 4, None, None) != 0          # invalid args are rejected
+
+
+def test_emu_shot_scores_with_halo(emu):
+    h = np.random.default_rng(0).integers(0, 100000, size=(70, 48)).astype(np.int32)
+    ref = restate.shot_scores(h)
+    S = np.zeros(70, np.int32)
+    assert emu.stb_shot_scores(P(h), 70, None, P(S), None) == 0
+    assert np.array_equal(S, ref)
+    S2 = np.zeros(69, np.int32)
+    assert emu.stb_shot_scores(P(h[1:]), 69, P(h[0]), P(S2), None) == 0
+    assert np.array_equal(S2, ref[1:])
+
+
+def test_emu_flow_histogram_edge_values(emu):
+    for (h, w) in [(17, 33), (60, 107)]:
+        ff = synth.textured_flow_field(3, h, w)
+        out = np.zeros(128, np.int32)
+        assert emu.stb_flow_hist(_lib.ptr_table([ff.ctypes.data]), 1, w, h, P(out), None) == 0
+        assert np.array_equal(out.reshape(2, 64), restate.flow_histogram(ff))
+
+
+def test_emu_frame_difference(emu):
+    a = synth.noise_clip(2, 2, 19, 23)
+    o = np.zeros_like(a[0])
+    assert emu.stb_frame_diff(P(a[0]), P(a[1]), P(o), o.size, None) == 0
+    assert np.array_equal(o, restate.frame_difference(a[0], a[1]))
+
+
+@pytest.mark.parametrize('h,w,pairs', [(120, 160, 1), (135, 240, 2), (67, 45, 1)])
+def test_emu_farneback_vs_oracle(emu, h, w, pairs):
+    clip = synth.textured_clip(3, pairs + 1, h, w)
+    hd = C.c_void_p()
+    assert emu.stb_farneback_create(w, h, pairs, None, C.byref(hd)) == 0
+    ws, hs = (C.c_int * 8)(), (C.c_int * 8)()
+    ns = emu.stb_farneback_levels(hd, ws, hs)
+    assert [(ws[k], hs[k]) for k in range(ns)] == restate.pyramid_info(w, h)
+    flows = [np.zeros((h, w, 2), np.float32) for _ in range(pairs)]
+    rc = emu.stb_farneback_run(hd, _lib.ptr_table([f.ctypes.data for f in clip]), pairs,
+                               _lib.ptr_table([f.ctypes.data for f in flows]), None)
+    assert rc == 0, emu.stb_last_error()
+    emu.stb_farneback_destroy(hd)
+    for i in range(pairs):
+        e = epe(flows[i], restate.optical_flow(clip[i], clip[i + 1]))
+        # north_star tolerance: mean EPE <= 1e-3 px, max <= 1e-2 px
+        assert e.mean() <= 1e-3 and e.max() <= 1e-2, (i, e.mean(), e.max())
+        assert e.max() < 1e-4   # in practice float32 agreement is ~1e-5 px
+
+
+def test_emu_pipe_host_path(emu):
+    h, w = 48, 64
+    clip = synth.textured_clip(5, 6, h, w)
+    p = C.c_void_p()
+    assert emu.stb_pipe_create(w, h, 2, 1, C.byref(p)) == 0
+    hist = np.zeros((6, 48), np.int32)
+    S = np.zeros(6, np.int32)
+    assert emu.stb_pipe_hist(p, P(clip), 6, P(hist), P(S)) == 0
+    ref = np.stack([restate.histogram(f).reshape(-1) for f in clip])
+    assert np.array_equal(hist, ref) and np.array_equal(S, restate.shot_scores(ref))
+    flow = np.zeros((5, h, w, 2), np.float32)
+    fh = np.zeros((5, 128), np.int32)
+    assert emu.stb_pipe_flow(p, P(clip), 5, P(flow), P(fh)) == 0
+    for i in range(5):
+        e = epe(flow[i], restate.optical_flow(clip[i], clip[i + 1]))
+        assert e.max() < 1e-4, (i, e.max())
+        assert np.array_equal(fh[i].reshape(2, 64), restate.flow_histogram(flow[i]))
+    emu.stb_pipe_destroy(p)

@@ -1,0 +1,257 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (via the ctypes wrappers in
+scannertools_b200.ops), against the oracle on identical seeded inputs.
+
+Tolerances (BASELINE.json north_star): histogram counts, scores and boundary indices bit-exact;
+Farneback flow mean EPE <= 1e-3 px and max EPE <= 1e-2 px; flow histograms within +-1 count per
+bin when computed from the GPU flow (bit-exact when computed from identical flow).
+Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+
+from conftest import epe
+from oracle import restate
+from scannertools_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+try:
+    from oracle import cv2_ops as cvo
+except Exception:  # cv2 missing on the box: fall back to the pinned restatement
+    cvo = None
+
+
+def o_hist(f):
+    return (cvo or restate).histogram(f)
+
+
+def o_flow(f0, f1):
+    return (cvo or restate).optical_flow(f0, f1)
+
+
+def o_flow_hist(f):
+    return (cvo or restate).flow_histogram(f)
+
+
+@pytest.fixture(scope='module')
+def torch():
+    import torch
+    assert torch.cuda.is_available(), 'gpu tests need a CUDA device'
+    return torch
+
+
+@pytest.fixture(scope='module')
+def ops(torch):
+    from scannertools_b200 import ops
+    return ops
+
+
+def dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ------------------------------------------------------------------ Histogram / shot scoring
+def test_histogram_goldens(torch, ops, golden):
+    g = golden('hist_small.npz')
+    for nme in [k[3:] for k in g.files if k.startswith('in_')]:
+        out = ops.histogram(dev(torch, g['in_' + nme])).cpu().numpy()
+        assert np.array_equal(out[0], g['out_' + nme]), nme
+
+
+@pytest.mark.parametrize('h,w', [(360, 640), (240, 426), (1080, 1920), (2160, 3840), (37, 53)])
+def test_histogram_bit_exact(torch, ops, h, w):
+    n = 3 if h * w > 10 ** 6 else 9
+    fr = synth.noise_clip(7, n, h, w)
+    fr[1] = 0           # constant frames: worst case for a shared table
+    fr[2] = 255
+    out = ops.histogram(dev(torch, fr)).cpu().numpy()
+    ref = np.stack([np.stack([np.bincount(f[..., c].reshape(-1) >> 4, minlength=16) for c in range(3)]) for f in fr])
+    assert np.array_equal(out, ref.astype(np.int32))
+    assert np.array_equal(out[0], o_hist(fr[0]))
+    assert (out.sum(axis=2) == h * w).all()
+
+
+def test_histogram_separate_and_unaligned_buffers(torch, ops):
+    h, w = 120, 213    # 3*w = 639 bytes per row: nothing is 4- or 16-byte aligned
+    fr = synth.noise_clip(3, 5, h, w)
+    big = torch.zeros(5 * (h * w * 3 + 64), dtype=torch.uint8, device='cuda')
+    views = []
+    for i in range(5):
+        off = i * (h * w * 3 + 64) + (1, 3, 8, 15, 0)[i]
+        v = big[off:off + h * w * 3].view(h, w, 3)
+        v.copy_(dev(torch, fr[i]))
+        views.append(v)
+    out = ops.histogram(views).cpu().numpy()
+    for i in range(5):
+        assert np.array_equal(out[i], o_hist(fr[i])), i
+
+
+def test_histogram_large_batch_chunks(torch, ops):
+    fr = synth.noise_clip(11, 150, 36, 64)    # > 64 frames: several pointer-table launches
+    out = ops.histogram([dev(torch, f) for f in fr]).cpu().numpy()
+    ref = np.stack([restate.histogram(f) for f in fr])
+    assert np.array_equal(out, ref)
+    assert ops.histogram(torch.zeros((0, 4, 4, 3), dtype=torch.uint8, device='cuda')).shape == (0, 3, 16)
+
+
+def test_shot_detection_c1_end_to_end(torch, ops, golden):
+    """BASELINE configs[0]: 1000 frames 640x360, 16 bins/channel; 7 planted cuts
+    (mirrors scannertools/tests/test_all.py:222-233)."""
+    from scannertools_b200 import shot_detection
+    g = golden('shot_c1.npz')
+    clip, cuts = synth.cut_clip(5, 1000, 360, 640, n_cuts=7)
+    d = dev(torch, clip)
+    hist = ops.histogram(d)
+    S = ops.shot_scores(hist)
+    hist_h, S_h = hist.cpu().numpy(), S.cpu().numpy()
+    assert np.array_equal(hist_h[0], o_hist(clip[0]))
+    if np.array_equal(clip[0], g['frame0']):            # same generator output as when goldens were made
+        assert np.array_equal(hist_h.reshape(1000, 48), g['hists'].reshape(1000, 48))
+        assert np.array_equal(S_h, g['scores'])
+    assert np.array_equal(S_h, restate.shot_scores(hist_h))
+    rows = shot_detection.shot_boundaries(None, scores=S_h)
+    assert rows[0] == cuts and len(rows[0]) == 7 and all(r is None for r in rows[1:])
+    # frame-range shards with a one-histogram halo give the same scores
+    S2 = ops.shot_scores(hist[500:], prev_hist=hist[499]).cpu().numpy()
+    assert np.array_equal(S2, S_h[500:])
+
+
+def test_host_pipe_histogram(torch, ops):
+    clip, cuts = synth.cut_clip(9, 70, 90, 160, n_cuts=3)
+    pipe = ops.Pipe(160, 90, max_batch=16)
+    pinned = torch.from_numpy(clip).pin_memory()
+    hist, S = pipe.histogram(pinned)
+    ref = np.stack([restate.histogram(f) for f in clip])
+    assert np.array_equal(hist, ref)
+    assert np.array_equal(S, restate.shot_scores(ref))
+    pipe.close()
+
+
+# ------------------------------------------------------------------ FlowHistogram / FrameDifference
+def test_flow_histogram_goldens_bit_exact(torch, ops, golden):
+    g = golden('flowhist.npz')
+    for nme in [k[3:] for k in g.files if k.startswith('in_')]:
+        out = ops.flow_histogram(dev(torch, g['in_' + nme])).cpu().numpy()
+        assert np.array_equal(out[0], g['out_' + nme]), nme
+
+
+def test_flow_histogram_1080p_and_drops(torch, ops):
+    f = synth.textured_flow_field(5, 1080, 1920)
+    out = ops.flow_histogram(dev(torch, f)).cpu().numpy()[0]
+    assert np.array_equal(out, o_flow_hist(f))
+    assert out[0].sum() < 1080 * 1920 and out[1].sum() < 1080 * 1920   # >=64 px and ==360 deg are dropped
+
+
+def test_frame_difference(torch, ops, golden):
+    g = golden('framediff.npz')
+    out = ops.frame_difference(dev(torch, g['prev']), dev(torch, g['cur'])).cpu().numpy()
+    assert np.array_equal(out, g['out'])
+    a = synth.noise_clip(4, 2, 1080, 1920)
+    out = ops.frame_difference(dev(torch, a[0]), dev(torch, a[1])).cpu().numpy()
+    assert np.array_equal(out, (a[1].astype(np.int16) - a[0].astype(np.int16)).astype(np.uint8))
+
+
+# ------------------------------------------------------------------ OpticalFlow
+FLOW_MEAN_TOL, FLOW_MAX_TOL = 1e-3, 1e-2   # px, north_star
+
+
+def check_flow(got, ref, tag):
+    e = epe(got, ref)
+    assert e.mean() <= FLOW_MEAN_TOL and e.max() <= FLOW_MAX_TOL, (tag, e.mean(), e.max())
+    return e
+
+
+def test_farneback_goldens(torch, ops, golden):
+    g = golden('flow_small.npz')
+    for c in ['160x120', '240x135', '344x260']:
+        f0, f1 = g['f0_' + c], g['f1_' + c]
+        of = ops.OpticalFlow(f0.shape[1], f0.shape[0], max_batch=1)
+        out = of.execute(dev(torch, np.stack([f0, f1]))).cpu().numpy()
+        check_flow(out[0], g['flow_' + c], c)
+        of.close()
+
+
+def test_farneback_stage_by_stage(torch, ops):
+    """I_k, R_k, M and per-level flow against the C restatement's dumps at every scale."""
+    h, w = 260, 344
+    clip = synth.textured_clip(3, 2, h, w)
+    of = ops.OpticalFlow(w, h, max_batch=1)
+    for k in range(len(of.levels())):
+        _, d = of.debug_level(dev(torch, clip), k)
+        _, r = restate.farneback(restate.gray(clip[0]), restate.gray(clip[1]), dump_level=k)
+        assert np.abs(d['I0'].cpu().numpy() - r['I0']).max() < 1e-3
+        for nm in ('R0', 'R1', 'M0'):
+            got = d[nm].cpu().numpy()
+            ref = r[nm].transpose(2, 0, 1)
+            assert np.abs(got - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), (k, nm)
+        check_flow(d['flow'].cpu().numpy(), r['flow'], 'level %d' % k)
+    of.close()
+
+
+@pytest.mark.parametrize('h,w,seed', [(480, 640, 1), (240, 426, 7), (720, 1280, 2), (1080, 1920, 3)])
+def test_farneback_parity_sizes(torch, ops, h, w, seed):
+    """C2 (640x480) and the other BASELINE resolutions; 426x240 runs 3 scales only."""
+    clip = synth.textured_clip(seed, 3, h, w)
+    of = ops.OpticalFlow(w, h, max_batch=2)
+    out = of.execute(dev(torch, clip)).cpu().numpy()
+    assert out.dtype == np.float32 and out.shape == (2, h, w, 2)     # tests/test_all.py:173-177
+    for i in range(2):
+        ref = o_flow(clip[i], clip[i + 1])
+        check_flow(out[i], ref, (h, w, i))
+        # +-1 count per bin when the histogram is taken from the GPU flow
+        gh = ops.flow_histogram(dev(torch, out[i])).cpu().numpy()[0]
+        assert np.abs(gh.astype(np.int64) - o_flow_hist(ref)).max() <= 1, (h, w, i)
+    of.close()
+
+
+def test_farneback_batch_chunking_and_separate_buffers(torch, ops):
+    """9 pairs at 160x120: several level chunks, B+1 separate frame buffers, results must not
+    depend on batching (each pair equals its single-pair run bit for bit)."""
+    h, w = 120, 160
+    clip = synth.textured_clip(4, 10, h, w)
+    frames = [dev(torch, f) for f in clip]
+    of = ops.OpticalFlow(w, h, max_batch=9)
+    out = of.execute(frames).cpu().numpy()
+    of1 = ops.OpticalFlow(w, h, max_batch=1)
+    for i in range(9):
+        single = of1.execute(frames[i:i + 2]).cpu().numpy()[0]
+        assert np.array_equal(out[i], single), i
+        check_flow(out[i], o_flow(clip[i], clip[i + 1]), i)
+    with pytest.raises(ValueError):
+        of1.execute(frames[:3])
+    of.close(); of1.close()
+
+
+def test_farneback_content_classes(torch, ops):
+    """i.i.d. noise and flat + moving square (SURVEY Appendix A sensitivity cases)."""
+    h, w = 240, 320
+    rng = np.random.default_rng(0)
+    noise = rng.integers(0, 256, size=(2, h, w, 3), dtype=np.uint8)
+    flat = np.full((2, h, w, 3), 90, np.uint8)
+    flat[0, 100:140, 100:140] = 200
+    flat[1, 102:142, 103:143] = 200
+    of = ops.OpticalFlow(w, h, max_batch=1)
+    for tag, clip in (('noise', noise), ('square', flat)):
+        out = of.execute(dev(torch, clip)).cpu().numpy()[0]
+        check_flow(out, o_flow(clip[0], clip[1]), tag)
+    # identical frames -> exactly zero flow
+    same = np.stack([noise[0], noise[0]])
+    assert not of.execute(dev(torch, same)).cpu().numpy().any()
+    of.close()
+
+
+def test_fused_flow_histogram_and_host_pipe(torch, ops):
+    h, w = 240, 426    # the shipped flow-histogram pipeline's resolution (old/histograms.py:64-68)
+    clip = synth.textured_clip(7, 6, h, w)
+    of = ops.OpticalFlow(w, h, max_batch=5)
+    flow, fh = of.execute_with_histogram(dev(torch, clip))
+    flow_h, fh_h = flow.cpu().numpy(), fh.cpu().numpy()
+    _, fh_only = of.execute_with_histogram(dev(torch, clip), want_flow=False)
+    assert np.array_equal(fh_only.cpu().numpy(), fh_h)
+    for i in range(5):
+        assert np.array_equal(fh_h[i], restate.flow_histogram(flow_h[i]))        # exact on identical flow
+        assert np.abs(fh_h[i].astype(np.int64) - o_flow_hist(o_flow(clip[i], clip[i + 1]))).max() <= 1
+    of.close()
+    pipe = ops.Pipe(w, h, max_batch=2, want_flow=True)       # batches of 2 pairs -> 3 batches with halo reuse
+    pf, ph = pipe.flow(torch.from_numpy(clip).pin_memory(), want_flow=True, want_hist=True)
+    assert np.array_equal(pf, flow_h) and np.array_equal(ph, fh_h)
+    pipe.close()

@@ -1,0 +1,82 @@
+"""Pins the oracle (test infrastructure) before it is trusted:
+  * the plain-C restatement (oracle/restate.c) against the committed goldens, which were
+    produced by OpenCV itself through cv2 (tests/golden/make_golden.py);
+  * when cv2 is importable, cv2 live against the same goldens (guards against a cv2 version
+    drift between the container that made the fixtures and the box that replays them)."""
+import numpy as np
+import pytest
+
+from conftest import epe
+from oracle import restate
+
+FLOW_CASES = ['160x120', '240x135', '344x260']
+
+
+def test_restate_gray(golden):
+    g = golden('flow_small.npz')
+    for c in FLOW_CASES:
+        assert np.array_equal(restate.gray(g['f0_' + c]), g['gray0_' + c])
+
+
+def test_restate_histogram(golden):
+    g = golden('hist_small.npz')
+    names = [k[3:] for k in g.files if k.startswith('in_')]
+    assert len(names) >= 5
+    for nme in names:
+        assert np.array_equal(restate.histogram(g['in_' + nme]), g['out_' + nme]), nme
+
+
+def test_restate_shot_c1(golden):
+    g = golden('shot_c1.npz')
+    assert np.array_equal(restate.histogram(g['frame0']).reshape(-1), g['hists'][0].reshape(-1))
+    c0 = int(g['cuts'][0])
+    assert np.array_equal(restate.histogram(g['frame_first_cut']).reshape(-1), g['hists'][c0].reshape(-1))
+    assert np.array_equal(restate.shot_scores(g['hists']), g['scores'])
+    assert list(g['boundaries']) == list(g['cuts']) and len(g['cuts']) == 7
+
+
+def test_restate_farneback(golden):
+    g = golden('flow_small.npz')
+    for c in FLOW_CASES:
+        fl = restate.optical_flow(g['f0_' + c], g['f1_' + c])
+        e = epe(fl, g['flow_' + c])
+        assert e.mean() < 1e-5 and e.max() < 1e-4, (c, e.mean(), e.max())
+
+
+def test_restate_pyramid_geometry():
+    # round-half-even level sizes, up to 4 scales
+    assert restate.pyramid_info(640, 480) == [(640, 480), (320, 240), (160, 120), (80, 60)]
+    assert restate.pyramid_info(1920, 1080) == [(1920, 1080), (960, 540), (480, 270), (240, 135)]
+    assert restate.pyramid_info(426, 240) == [(426, 240), (213, 120), (106, 60)]
+    assert restate.pyramid_info(344, 260)[-1] == (43, 32)
+
+
+def test_restate_flow_histogram(golden):
+    g = golden('flowhist.npz')
+    names = [k[3:] for k in g.files if k.startswith('in_')]
+    for nme in names:
+        assert np.array_equal(restate.flow_histogram(g['in_' + nme]), g['out_' + nme]), nme
+    mag, deg = restate.polar(g['in_stress_33x17'])
+    assert np.array_equal(mag, g['mag_stress_33x17'])
+    assert np.array_equal(deg, g['deg_stress_33x17'])
+
+
+def test_restate_frame_difference(golden):
+    g = golden('framediff.npz')
+    assert np.array_equal(restate.frame_difference(g['prev'], g['cur']), g['out'])
+
+
+def test_cv2_matches_goldens(golden, have_cv2):
+    if not have_cv2:
+        pytest.skip('cv2 not importable')
+    from oracle import cv2_ops
+    g = golden('flow_small.npz')
+    for c in FLOW_CASES[:2]:
+        e = epe(cv2_ops.optical_flow(g['f0_' + c], g['f1_' + c]), g['flow_' + c])
+        assert e.max() < 1e-4, (c, e.max())
+    gh = golden('hist_small.npz')
+    assert np.array_equal(cv2_ops.histogram(gh['in_noise_37x53']), gh['out_noise_37x53'])
+    gf = golden('flowhist.npz')
+    assert np.array_equal(cv2_ops.flow_histogram(gf['in_stress_213x120']), gf['out_stress_213x120'])
+    gs = golden('shot_c1.npz')
+    assert cv2_ops.shot_boundaries(list(gs['hists'].reshape(-1, 3, 16))) == list(gs['boundaries'])
