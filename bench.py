@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""Benchmark of the per-frame analysis hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA kernels via the C ABI)
+  python bench.py --impl reference ...                      reference arm: the reference's OpenCV
+                                                            CPU ops on the box's host cores
+
+Headline workload (config.workload): C3 -- 1080p Farneback OpticalFlow + FlowHistogram, the
+configuration the metric is quoted on.  A "step" is one pass of the hot path over one batch of
+`--pairs` frame pairs (pairs+1 synthetic 1080p RGB frames of a ring larger than L2).
+`value`  = frames/s with the frames already resident in HBM (whole job, all ranks).
+`e2e`    = frames/s through the host-buffer C-ABI call (stb_pipe_flow): pinned-host frames in,
+           H2D copies inside the timed region, 512-byte flow histograms out.
+`roofline` = the dominant kernel (fused level-0 update iteration): algorithmic bytes per launch
+           / its CUDA-event duration measured in the timed region, against MEASURED_PEAKS.json.
+`extra`  = secondary workloads of the metric (4K RGB histogram + shot scoring; C2 640x480 flow).
+Frames are independent: ranks own disjoint frame ranges, no collective on the data path
+(scaling = weak: per-GPU work is fixed).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic bytes (SURVEY.md §8d / DESIGN.md "Byte model")
+FLOW1080_BYTES = 771768000          # canonical Farneback pass model, per 1080p frame
+FLOWHIST1080_BYTES = 16589312       # 8*W*H + 512
+ITER_BYTES_PER_PX = 80              # level-0 update iteration: read M, R0, R1; write M' (5 f32 each)
+HIST4K_BYTES = 24883392             # 3*W*H + 192
+FLOW480_BYTES = 114336000
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured'
+        except Exception:
+            pass
+    return 6650.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(nme)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------ reference arm
+def _cpu_worker(args):
+    kind, h, w, seed, reps = args
+    import cv2
+    cv2.setNumThreads(1)   # Farneback does not scale with OpenCV threads: one worker per core
+    from oracle import cv2_ops
+    from scannertools_b200 import synth
+    if kind == 'flow':
+        clip = synth.textured_clip(seed, 2, h, w)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fl = cv2_ops.optical_flow(clip[0], clip[1])
+            cv2_ops.flow_histogram(fl)
+        return reps, time.perf_counter() - t0
+    clip = synth.noise_clip(seed, 2, h, w)
+    t0 = time.perf_counter()
+    for i in range(reps):
+        cv2_ops.histogram(clip[i & 1])
+    return reps, time.perf_counter() - t0
+
+
+def cpu_pass(pool, cores, kind, h, w, reps):
+    t0 = time.perf_counter()
+    res = pool.map(_cpu_worker, [(kind, h, w, 100 + c, reps) for c in range(cores)])
+    wall = time.perf_counter() - t0
+    frames = sum(r[0] for r in res)
+    return frames, wall
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path: the OpenCV calls its C++ wrappers
+    make (oracle/cv2_ops.py), one worker process per host core on disjoint frames."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = host_cores()
+    ctx = mp.get_context('fork')
+    with ctx.Pool(cores) as pool:
+        cpu_pass(pool, cores, 'flow', 1080, 1920, 1)          # spawn + page-in warm-up
+        for _ in range(max(args.warmup - 1, 0)):
+            cpu_pass(pool, cores, 'flow', 1080, 1920, 1)
+        frames, wall = 0, 0.0
+        for _ in range(args.steps):
+            f, wl = cpu_pass(pool, cores, 'flow', 1080, 1920, 1)
+            frames += f
+            wall += wl
+    fps = frames / wall
+    sample = '%d steps x %d workers x 1 1080p pair each (cv2 %s: cvtColor+Farneback+cartToPolar+calcHist)' % (
+        args.steps, cores, __import__('cv2').__version__)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * wall / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args),
+        'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+METRIC = '1080p Farneback OpticalFlow + FlowHistogram throughput'
+
+
+def workload_config(args):
+    return {'workload': 'C3: 1080p (1920x1080) Farneback optical flow (3 levels, winsize 15, 3 iters, polyN 5) + '
+                        'FlowHistogram, synthetic textured clip, frame-range sharded',
+            'pairs_per_step': args.pairs, 'batch_pairs': args.batch, 'frame': '1920x1080x3 u8',
+            'l2_policy': 'inputs larger than L2: ring of %d distinct frames (%.0f MB) + %.0f MB of flow output per step'
+                         % (args.pairs + 1, (args.pairs + 1) * 6.2208, args.pairs * 16.5888),
+            'parallelism': 'frame-range x%d, no collective' % args.gpus}
+
+
+# ------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from scannertools_b200 import _lib, ops, synth
+    import ctypes as C
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; scannertools_b200 has no CPU fallback '
+                         '(use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    lib = _lib.load()
+    H, W = 1080, 1920
+    P, B = args.pairs, args.batch
+    assert P % B == 0, '--pairs must be a multiple of --batch'
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- synthetic clip: this rank's frame range (different content per rank), ring > L2
+    clip = synth.textured_clip(1000 + rank, P + 1, H, W)
+    host = torch.from_numpy(clip).pin_memory()
+    d_frames = host.cuda(non_blocking=True)
+    torch.cuda.synchronize()
+    of = ops.OpticalFlow(W, H, max_batch=B)
+    d_flow = torch.empty((P, H, W, 2), dtype=torch.float32, device='cuda')
+    d_fh = torch.empty((P, 2, 64), dtype=torch.int32, device='cuda')
+    frame_ptrs = [d_frames[i].data_ptr() for i in range(P + 1)]
+    flow_ptrs = [d_flow[i].data_ptr() for i in range(P)]
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+
+    def step_device():
+        for b0 in range(0, P, B):
+            ft = _lib.ptr_table(frame_ptrs[b0:b0 + B + 1])
+            ot = _lib.ptr_table(flow_ptrs[b0:b0 + B])
+            _lib.check(lib.stb_farneback_run_hist(of._h, ft, B, ot, C.c_void_p(d_fh[b0].data_ptr()), sp), lib)
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.stb_farneback_profile(of._h, 1)
+    l0 = lib.stb_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step_device()
+    ev1.record()
+    barrier()
+    t_dev = ev0.elapsed_time(ev1) * 1e-3
+    launches = lib.stb_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total, nl = C.c_double(), C.c_longlong()
+    _lib.check(lib.stb_farneback_profile_read(of._h, C.byref(ms_total), C.byref(nl)), lib)
+    lib.stb_farneback_profile(of._h, 0)
+    fh_dev = d_fh.cpu().numpy().copy()
+
+    # ---- e2e: host frames in (pinned), flow histograms out, through stb_pipe_flow
+    pipe = ops.Pipe(W, H, max_batch=B, want_flow=True)
+    for _ in range(max(1, args.warmup // 2)):
+        _, fh_e2e = pipe.flow(host, want_flow=False, want_hist=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, fh_e2e = pipe.flow(host, want_flow=False, want_hist=True)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    barrier()
+    assert np.array_equal(fh_e2e, fh_dev), 'e2e and device-resident paths disagree'
+
+    # ---- max over ranks (timing scalars only; no data-path collective)
+    times = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device='cuda')
+    stats = torch.tensor([float(launches), ms_total.value, float(nl.value)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    t_dev, t_e2e = times.tolist()
+    launches_all, ms_iter_all, nl_all = stats.tolist()
+
+    extra = {}
+    if rank == 0 and world == 1 and not args.no_extra:
+        extra = extra_workloads(torch, ops, lib, args)
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu_base = cpu_baseline()
+
+    if rank == 0:
+        peak, peak_kind = measured_peaks()
+        total_frames = world * args.steps * P
+        iter_bytes = ITER_BYTES_PER_PX * H * W          # one pair per launch at level 0
+        avg_iter_s = (ms_iter_all / nl_all) * 1e-3 if nl_all else float('nan')
+        achieved = iter_bytes / avg_iter_s / 1e9 if nl_all else None
+        value = total_frames / t_dev
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * t_dev / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args),
+            'hbm_roofline_frac_whole_op': (FLOW1080_BYTES + FLOWHIST1080_BYTES) * value / world / (peak * 1e9),
+            'roofline': {'bound': 'hbm', 'kernel': 'iter_kernel<true> (level-0 fused box-sum/solve/update-matrices)',
+                         'achieved': achieved, 'peak': peak, 'peak_kind': peak_kind, 'unit': 'GB/s',
+                         'frac': (achieved / peak) if achieved else None,
+                         'bytes_per_launch': iter_bytes, 'avg_launch_us': avg_iter_s * 1e6, 'launches_timed': int(nl_all),
+                         'share_of_step': (ms_iter_all * 1e-3 / world) / t_dev if t_dev else None,
+                         'traffic': NCU_TRAFFIC_BYTES},
+            'e2e': {'value': total_frames / t_e2e, 'unit': 'frames/s',
+                    'h2d_bytes_per_step': world * (P + 1) * H * W * 3 - world * (P // B - 1) * H * W * 3 * 0,
+                    'd2h_bytes_per_step': world * P * 512, 'ms_per_step': 1e3 * t_e2e / args.steps,
+                    'api': 'stb_pipe_flow (host frames -> flow histograms)'},
+            'gpu_launches': int(launches_all),
+            'clocks': clocks,
+            'cpu_baseline': cpu_base,
+            'extra': extra,
+        }
+        print(json.dumps(line))
+    of.close()
+    pipe.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one iter_kernel<true> level-0 launch from the
+# committed `ncu --set full` capture (profiles/); None until a capture exists.
+NCU_TRAFFIC_BYTES = None
+
+
+def extra_workloads(torch, ops, lib, args):
+    """Secondary workloads named by the metric, device-resident + e2e, short loops."""
+    import ctypes as C
+    from scannertools_b200 import _lib
+    peak, _ = measured_peaks()
+    out = {}
+
+    def time_dev(fn, iters, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e-3 / iters
+
+    # C4: 4K RGB histogram + shot scores, 32 frames per step (796 MB > L2)
+    n4k = 32
+    fr = torch.randint(0, 256, (n4k, 2160, 3840, 3), dtype=torch.uint8, device='cuda')
+    t = time_dev(lambda: ops.shot_scores(ops.histogram(fr)), 10)
+    host4k = fr.cpu().pin_memory()
+    pipe = ops.Pipe(3840, 2160, max_batch=7)
+    pipe.histogram(host4k)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        pipe.histogram(host4k)
+    te = (time.perf_counter() - t0) / 3
+    pipe.close()
+    out['hist4k'] = {'workload': 'C4: 3840x2160 RGB histogram (16 bins/channel) + shot scores, 32 frames/step, i.i.d. noise',
+                     'value': n4k / t, 'unit': 'frames/s', 'ms_per_step': t * 1e3,
+                     'roofline': {'bound': 'hbm', 'achieved': n4k * HIST4K_BYTES / t / 1e9, 'peak': peak, 'unit': 'GB/s',
+                                  'frac': n4k * HIST4K_BYTES / t / 1e9 / peak},
+                     'e2e': {'value': n4k / te, 'unit': 'frames/s', 'h2d_bytes_per_step': n4k * 3840 * 2160 * 3,
+                             'd2h_bytes_per_step': n4k * 196}}
+    del fr, host4k
+    # C2: 640x480 Farneback, 16 pairs per step
+    from scannertools_b200 import synth
+    clip = synth.textured_clip(2, 17, 480, 640)
+    d = torch.from_numpy(clip).cuda()
+    of = ops.OpticalFlow(640, 480, max_batch=16)
+    o = torch.empty((16, 480, 640, 2), dtype=torch.float32, device='cuda')
+    t = time_dev(lambda: of.execute(d, out=o), 10)
+    of.close()
+    out['flow480'] = {'workload': 'C2: 640x480 Farneback, 16 pairs/step', 'value': 16 / t, 'unit': 'frames/s',
+                      'ms_per_step': t * 1e3,
+                      'roofline': {'bound': 'hbm', 'achieved': 16 * FLOW480_BYTES / t / 1e9, 'peak': peak, 'unit': 'GB/s',
+                                   'frac': 16 * FLOW480_BYTES / t / 1e9 / peak}}
+    return out
+
+
+def cpu_baseline():
+    """Reference CPU ops (cv2) on this box's host cores: bounded sample, one worker per core."""
+    import multiprocessing as mp
+    cores = host_cores()
+    ctx = mp.get_context('fork')
+    with ctx.Pool(cores) as pool:
+        cpu_pass(pool, cores, 'flow', 1080, 1920, 1)
+        reps = 2
+        frames, wall = cpu_pass(pool, cores, 'flow', 1080, 1920, reps)
+        hframes, hwall = cpu_pass(pool, cores, 'hist', 2160, 3840, 8)
+    import cv2
+    return {'value': frames / wall, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+            'sample': '%d workers x %d 1080p pairs: cv2 %s cvtColor+Farneback(3,0.5,15,3,5,1.2)+cartToPolar+2xcalcHist, '
+                      'cv2.setNumThreads(1) per worker' % (cores, reps, cv2.__version__),
+            'hist4k_frames_per_s': hframes / hwall}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--pairs', type=int, default=32, help='frame pairs per step')
+    ap.add_argument('--batch', type=int, default=16, help='pairs per C-ABI batch call')
+    ap.add_argument('--no-extra', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

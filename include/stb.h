@@ -142,6 +142,16 @@ STB_API int stb_farneback_levels(const stb_farneback* h, int* widths /* 8 */, in
 STB_API int stb_farneback_debug_set(stb_farneback* h, int level, int pair, float* d_I0, float* d_I1,
                                     float* d_R0, float* d_R1, float* d_M0, float* d_flow_level);
 
+/* ---- measurement hooks (bench.py) -----------------------------------------------------------
+ * stb_launch_count: kernels this library has launched in this process (all entry points).
+ * stb_farneback_profile: when enabled, every level-0 pair brackets its fused update-iteration
+ * kernels (the dominant kernel) with CUDA events on the launching stream;
+ * _profile_read synchronises those events and returns their summed duration and the number of
+ * kernel launches they cover. */
+STB_API long long stb_launch_count(void);
+STB_API int stb_farneback_profile(stb_farneback* h, int enable);
+STB_API int stb_farneback_profile_read(stb_farneback* h, double* ms_total, long long* launches);
+
 /* ---- host-buffer entry points (end-to-end path) ---------------------------------------------
  * The reference's kernels receive device frames from the Scanner engine; when this library is
  * driven directly with HOST frames (bench e2e, python wrappers on numpy arrays) these calls own

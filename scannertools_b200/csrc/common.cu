@@ -6,6 +6,9 @@
 namespace stb {
 
 static thread_local char g_err[512] = "";
+#ifndef STB_CPU_EMU
+std::atomic<long long> g_launches{0};
+#endif
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -28,6 +31,14 @@ extern "C" {
 int stb_version(void) { return 100; }
 
 const char* stb_last_error(void) { return stb::g_err; }
+
+long long stb_launch_count(void) {
+#ifndef STB_CPU_EMU
+  return stb::g_launches.load(std::memory_order_relaxed);
+#else
+  return 0;
+#endif
+}
 
 int stb_device_count(void) {
   int n = 0;

@@ -24,6 +24,7 @@
 #include <cmath>
 #include <cstring>
 #include <new>
+#include <vector>
 
 namespace stb {
 
@@ -470,6 +471,11 @@ struct stb_farneback {
   // debug taps
   int dbg_level, dbg_pair;
   float *dbg_I0, *dbg_I1, *dbg_R0, *dbg_R1, *dbg_M0, *dbg_flow;
+  // measurement hook: event pairs around the level-0 update-iteration kernels
+  int profile;
+  std::vector<cudaEvent_t> ev_free;
+  std::vector<cudaEvent_t> ev_used;   // (begin, end) pairs
+  long long prof_launches;
 };
 
 namespace stb {
@@ -622,7 +628,6 @@ int stb_farneback_create(int width, int height, int max_pairs, const stb_farneba
   if (rc) return rc;
   stb_farneback* h = new (std::nothrow) stb_farneback();
   if (!h) { set_error("stb_farneback_create: out of host memory"); return STB_ERR_ALLOC; }
-  std::memset(h, 0, sizeof(*h));
   h->W = width; h->H = height; h->max_pairs = max_pairs; h->prm = p; h->dbg_level = -1;
   h->device = current_device();
   h->nscales = plan_levels(width, height, p, h->w, h->h);
@@ -688,6 +693,8 @@ int stb_farneback_destroy(stb_farneback* h) {
   if (!h) return STB_OK;
   if (h->gray) cudaFree(h->gray);
   if (h->flow0) cudaFree(h->flow0);
+  for (cudaEvent_t e : h->ev_free) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->ev_used) cudaEventDestroy(e);
   delete h;
   return STB_OK;
 }
@@ -701,6 +708,29 @@ int stb_farneback_levels(const stb_farneback* h, int* widths, int* heights) {
   return h->nscales;
 }
 
+int stb_farneback_profile(stb_farneback* h, int enable) {
+  if (!h) { set_error("stb_farneback_profile: NULL handle"); return STB_ERR_INVALID; }
+  h->profile = enable ? 1 : 0;
+  return STB_OK;
+}
+
+int stb_farneback_profile_read(stb_farneback* h, double* ms_total, long long* launches) {
+  if (!h) { set_error("stb_farneback_profile_read: NULL handle"); return STB_ERR_INVALID; }
+  double total = 0;
+  for (size_t i = 0; i + 1 < h->ev_used.size(); i += 2) {
+    float ms = 0;
+    STB_CUDA(cudaEventSynchronize(h->ev_used[i + 1]));
+    STB_CUDA(cudaEventElapsedTime(&ms, h->ev_used[i], h->ev_used[i + 1]));
+    total += ms;
+  }
+  for (cudaEvent_t e : h->ev_used) h->ev_free.push_back(e);
+  h->ev_used.clear();
+  if (ms_total) *ms_total = total;
+  if (launches) *launches = h->prof_launches;
+  h->prof_launches = 0;
+  return STB_OK;
+}
+
 int stb_farneback_debug_set(stb_farneback* h, int level, int pair, float* d_I0, float* d_I1, float* d_R0, float* d_R1,
                             float* d_M0, float* d_flow_level) {
   if (!h) { set_error("stb_farneback_debug_set: NULL handle"); return STB_ERR_INVALID; }
@@ -712,6 +742,15 @@ int stb_farneback_debug_set(stb_farneback* h, int level, int pair, float* d_I0, 
 }  // extern "C"
 
 namespace stb {
+
+static int prof_mark(stb_farneback* h, cudaStream_t s) {
+  cudaEvent_t e;
+  if (!h->ev_free.empty()) { e = h->ev_free.back(); h->ev_free.pop_back(); }
+  else STB_CUDA(cudaEventCreate(&e));
+  h->ev_used.push_back(e);
+  STB_CUDA(cudaEventRecord(e, s));
+  return STB_OK;
+}
 
 static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_t s) {
   const int F = n + 1;
@@ -760,11 +799,18 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
         fo.p[i] = (k == 0) ? d_flow[p0 + i] : h->flow[fl_cur] + (size_t)(p0 + i) * nk * 2;
       int mc = 0;
       const dim3 grid(ceil_div(w, kItTW), ceil_div(hh, kItTH), np);
+      const bool prof = h->profile && k == 0 && h->prm.num_iters > 1;
       for (int it = 0; it < h->prm.num_iters; ++it) {
         if (it < h->prm.num_iters - 1) {
+          if (prof && it == 0) { int prc = prof_mark(h, s); if (prc) return prc; }
           stb_launch(iter_kernel<true>, grid, dim3(kItThreads), it_smem, s, (const float*)h->M[mc], h->M[mc ^ 1],
                      (const float*)h->R, fo, w, hh, m, p0);
           mc ^= 1;
+          if (prof && it == h->prm.num_iters - 2) {
+            int prc = prof_mark(h, s);
+            if (prc) return prc;
+            h->prof_launches += h->prm.num_iters - 1;
+          }
         } else {
           stb_launch(iter_kernel<false>, grid, dim3(kItThreads), it_smem, s, (const float*)h->M[mc], (float*)nullptr,
                      (const float*)h->R, fo, w, hh, m, p0);

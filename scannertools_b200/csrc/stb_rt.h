@@ -15,9 +15,12 @@
 #include "stb.h"
 
 #ifndef STB_CPU_EMU
+#include <atomic>
+namespace stb { extern std::atomic<long long> g_launches; }
 template <class... KArgs, class... Args>
 static inline void stb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
   kernel<<<grid, block, smem, s>>>(args...);
+  stb::g_launches.fetch_add(1, std::memory_order_relaxed);
 }
 #define STB_DYN_SMEM(T, name)                                      \
   extern __shared__ __align__(16) unsigned char stb_dyn_smem_[];   \
