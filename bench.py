@@ -142,7 +142,7 @@ def run_reference(args):
         return
     import multiprocessing as mp
     cores = host_cores()
-    ctx = mp.get_context('fork')
+    ctx = mp.get_context('spawn')
     with ctx.Pool(cores) as pool:
         cpu_pass(pool, cores, 'flow', 1080, 1920, 1)          # spawn + page-in warm-up
         for _ in range(max(args.warmup - 1, 0)):
@@ -370,20 +370,33 @@ def extra_workloads(torch, ops, lib, args):
 
 
 def cpu_baseline():
-    """Reference CPU ops (cv2) on this box's host cores: bounded sample, one worker per core."""
+    """Reference CPU ops (cv2) on this box's host cores, in a child process that never touches
+    CUDA (forking/spawning workers from a process with a live CUDA context is avoided)."""
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), '--cpu-baseline-child'], capture_output=True,
+                             text=True, timeout=300)
+        for line in out.stdout.splitlines():
+            if line.startswith('{'):
+                return json.loads(line)
+        return {'error': (out.stderr or 'no output')[-300:]}
+    except Exception as e:  # noqa: BLE001
+        return {'error': repr(e)}
+
+
+def cpu_baseline_child():
     import multiprocessing as mp
     cores = host_cores()
-    ctx = mp.get_context('fork')
+    ctx = mp.get_context('spawn')
     with ctx.Pool(cores) as pool:
         cpu_pass(pool, cores, 'flow', 1080, 1920, 1)
         reps = 2
         frames, wall = cpu_pass(pool, cores, 'flow', 1080, 1920, reps)
         hframes, hwall = cpu_pass(pool, cores, 'hist', 2160, 3840, 8)
     import cv2
-    return {'value': frames / wall, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-            'sample': '%d workers x %d 1080p pairs: cv2 %s cvtColor+Farneback(3,0.5,15,3,5,1.2)+cartToPolar+2xcalcHist, '
-                      'cv2.setNumThreads(1) per worker' % (cores, reps, cv2.__version__),
-            'hist4k_frames_per_s': hframes / hwall}
+    print(json.dumps({'value': frames / wall, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+                      'sample': '%d workers x %d 1080p pairs: cv2 %s cvtColor+Farneback(3,0.5,15,3,5,1.2)+cartToPolar+2xcalcHist, '
+                                'cv2.setNumThreads(1) per worker' % (cores, reps, cv2.__version__),
+                      'hist4k_frames_per_s': hframes / hwall}))
 
 
 def main():
@@ -396,7 +409,11 @@ def main():
     ap.add_argument('--batch', type=int, default=16, help='pairs per C-ABI batch call')
     ap.add_argument('--no-extra', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--cpu-baseline-child', action='store_true', help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_baseline_child:
+        cpu_baseline_child()
+        return
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == 'reference':

@@ -122,7 +122,10 @@ __device__ __forceinline__ void resize_src(int d, double scale, int n_src, int& 
 __global__ void __launch_bounds__(kPyrThreads)
 pyr_kernel(const uint8_t* __restrict__ gray, float* __restrict__ I, PyrParams p, int frame0) {
   STB_DYN_SMEM(float, hx);  // [max_rows][32]
+  __shared__ float taps[kMaxGaussTaps];
   const int tid = threadIdx.x;
+  if (tid < kMaxGaussTaps) taps[tid] = p.taps[tid];
+  __syncthreads();
   const int frame = frame0 + blockIdx.z;
   const uint8_t* G = gray + (size_t)frame * p.W * p.H;
   float* out = I + (size_t)frame * p.w * p.h;
@@ -145,9 +148,9 @@ pyr_kernel(const uint8_t* __restrict__ gray, float* __restrict__ I, PyrParams p,
       if (x < p.w) {
         const uint8_t* row = G + (size_t)reflect101(row_lo + rr, p.H) * p.W;
         float a = 0.f, b = 0.f;
-        for (int t = 0; t <= 2 * p.r; ++t) a = fmaf(p.taps[t], (float)row[reflect101(sx + t - p.r, p.W)], a);
+        for (int t = 0; t <= 2 * p.r; ++t) a = fmaf(taps[t], (float)row[reflect101(sx + t - p.r, p.W)], a);
         if (fx != 0.f)
-          for (int t = 0; t <= 2 * p.r; ++t) b = fmaf(p.taps[t], (float)row[reflect101(sx + 1 + t - p.r, p.W)], b);
+          for (int t = 0; t <= 2 * p.r; ++t) b = fmaf(taps[t], (float)row[reflect101(sx + 1 + t - p.r, p.W)], b);
         v = a * (1.f - fx) + b * fx;
       }
       hx[rr * kPyrTW + ox] = v;
@@ -163,10 +166,62 @@ pyr_kernel(const uint8_t* __restrict__ gray, float* __restrict__ I, PyrParams p,
       resize_src(oy, p.scale_y, p.H, sy, fy);
       const int base = sy - p.r - row_lo;  // >= 0 by construction
       float a = 0.f, b = 0.f;
-      for (int t = 0; t <= 2 * p.r; ++t) a = fmaf(p.taps[t], hx[(base + t) * kPyrTW + ox], a);
+      for (int t = 0; t <= 2 * p.r; ++t) a = fmaf(taps[t], hx[(base + t) * kPyrTW + ox], a);
       if (fy != 0.f)
-        for (int t = 0; t <= 2 * p.r; ++t) b = fmaf(p.taps[t], hx[(base + 1 + t) * kPyrTW + ox], b);
+        for (int t = 0; t <= 2 * p.r; ++t) b = fmaf(taps[t], hx[(base + 1 + t) * kPyrTW + ox], b);
       out[(size_t)oy * p.w + x] = a * (1.f - fy) + b * fy;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// level 0 of the pyramid: 3x3 separable Gaussian (taps t0,t1,t2; REFLECT_101), no resize.
+// Each thread produces a 4 (x) by 4 (y) patch: 6 source rows x (one aligned 4-byte load + the
+// two neighbouring bytes), horizontal blur per row, vertical combine, float4 stores.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pyr0_kernel(const uint8_t* __restrict__ gray, float* __restrict__ I, int W, int H, float t0, float t1, float t2,
+            int frame0, int vec_ok) {
+  const int frame = frame0 + blockIdx.z;
+  const uint8_t* G = gray + (size_t)frame * W * H;
+  float* out = I + (size_t)frame * W * H;
+  const int x0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
+  const int y0 = (blockIdx.y * 8 + (threadIdx.x >> 5)) * 4;
+  if (x0 >= W || y0 >= H) return;
+  const bool fast = vec_ok && (x0 + 4 <= W);
+  float hrow[6][4];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    const int y = reflect101(y0 - 1 + r, H);
+    const uint8_t* row = G + (size_t)y * W;
+    float g[6];
+    if (fast) {
+      const unsigned wd = __ldg(reinterpret_cast<const unsigned*>(row + x0));
+      g[1] = (float)(wd & 0xffu); g[2] = (float)((wd >> 8) & 0xffu);
+      g[3] = (float)((wd >> 16) & 0xffu); g[4] = (float)(wd >> 24);
+      g[0] = (float)__ldg(row + (x0 > 0 ? x0 - 1 : 1 % W));
+      g[5] = (float)__ldg(row + (x0 + 4 < W ? x0 + 4 : reflect101(x0 + 4, W)));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) g[i] = (float)__ldg(row + reflect101(x0 - 1 + i, W));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) hrow[r][i] = fmaf(t2, g[i + 2], fmaf(t1, g[i + 1], t0 * g[i]));
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int y = y0 + j;
+    if (y >= H) break;
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = fmaf(t2, hrow[j + 2][i], fmaf(t1, hrow[j + 1][i], t0 * hrow[j][i]));
+    float* dst = out + (size_t)y * W + x0;
+    if (fast) {
+      *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (x0 + i < W) dst[i] = o[i];
     }
   }
 }
@@ -411,7 +466,7 @@ iter_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const float
     const float nx = fmaf(g11, h2, -t1) + fmaf(-g12, h1, t1);
     const float t2 = g12 * h2;
     const float ny = fmaf(g22, h1, -t2) + fmaf(-g12, h2, t2);
-    fl[lane * kItTW + warp * 8 + i] = make_float2(nx * idet, ny * idet);
+    fl[lane * (kItTW + 1) + warp * 8 + i] = make_float2(nx * idet, ny * idet);
   }
   __syncthreads();
 
@@ -424,7 +479,7 @@ iter_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const float
       const int ty = (tid >> 6) + 4 * i;
       const int y = oy0 + ty;
       if (y >= h) break;
-      const float2 f = fl[ty * kItTW + tx];
+      const float2 f = fl[ty * (kItTW + 1) + tx];
       if (UPDATE) {
         float mm[5];
         update_matrices_px(R + (size_t)pair * 5 * n, R + (size_t)(pair + 1) * 5 * n, n, w, h, x, y, f.x, f.y, mm);
@@ -441,8 +496,139 @@ iter_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const float
 static inline size_t iter_smem_bytes(int m) {
   const int rawW = kItTW + 2 * m, rawH = kItTH + 2 * m;
   size_t box = ((size_t)rawH * (rawW + 2) + (size_t)rawW * 33) * sizeof(float);
-  size_t fl = (size_t)kItTW * kItTH * sizeof(float2);
+  size_t fl = (size_t)(kItTW + 1) * kItTH * sizeof(float2);
   return box > fl ? box : fl;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// The same iteration specialised for the reference's winSize = 15 (m = 7): the production path.
+// Differences from the generic kernel above:
+//   * no raw tile in shared memory: each thread item (column, 8-row group) pulls its 22 rows
+//     straight from global memory (coalesced along x; the 2.75x re-reads between row groups
+//     hit L1), forms the vertical sliding sums in registers and writes them transposed;
+//   * the loads of plane c+1 are issued before the barrier and the horizontal pass of plane c,
+//     so global latency overlaps shared-memory work (software pipeline, double-buffered Vt);
+//   * tile 48 x 32 makes every phase fill the 256 threads: vertical 62 cols x 4 groups = 248
+//     items, horizontal 32 rows x 8 groups of 6 columns = 256 items, update 6 pixels/thread;
+//   * one barrier per plane.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFiTW = 48, kFiTH = 32, kFiThreads = 256, kFiM = 7;
+constexpr int kFiRawW = kFiTW + 2 * kFiM;     // 62
+constexpr int kFiRows = 8 + 2 * kFiM;         // 22 input rows per vertical item
+constexpr int kFiGC = 6;                      // output columns per horizontal item
+constexpr int kFiVtWords = kFiRawW * 33;      // one transposed vertical-sum buffer
+constexpr int kFiFlStride = kFiTW + 1;        // float2 row stride of the staged flow (bank spread)
+
+template <bool UPDATE>
+__global__ void __launch_bounds__(kFiThreads, 3)
+iter15_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const float* __restrict__ R,
+              PtrBatch<float> flow_out, int w, int h, int pair0) {
+  __shared__ float Vt[2][kFiVtWords];
+  __shared__ float2 fl[kFiTH * kFiFlStride];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pair = pair0 + blockIdx.z;
+  const size_t n = (size_t)w * h;
+  const float* Mp = Min + (size_t)pair * 5 * n;
+  const int ox0 = blockIdx.x * kFiTW, oy0 = blockIdx.y * kFiTH;
+
+  // vertical item of this thread
+  const bool vact = tid < kFiRawW * 4;
+  const int vg = tid / kFiRawW, vcx = tid - vg * kFiRawW;
+  const int gx = min(max(ox0 + vcx - kFiM, 0), w - 1);
+  const int y_first = oy0 + vg * 8 - kFiM;
+  // row offsets are the same for every plane
+  const bool interior_rows = (y_first >= 0) && (y_first + kFiRows - 1 <= h - 1);
+  const float* col0 = Mp + (size_t)min(max(y_first, 0), h - 1) * w + gx;
+
+  float v[kFiRows];
+  auto load_plane = [&](int c) {
+    const float* pl = col0 + (size_t)c * n;
+    if (interior_rows) {
+#pragma unroll
+      for (int j = 0; j < kFiRows; ++j) v[j] = __ldg(pl + (size_t)j * w);
+    } else {
+      const float* base = Mp + (size_t)c * n + gx;
+#pragma unroll
+      for (int j = 0; j < kFiRows; ++j) v[j] = __ldg(base + (size_t)min(max(y_first + j, 0), h - 1) * w);
+    }
+  };
+
+  float sums[5][kFiGC];
+  if (vact) load_plane(0);
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    float* vt = Vt[c & 1];
+    if (vact) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 15; ++j) s += v[j];
+      float* o = vt + vcx * 33 + vg * 8;
+      o[0] = s;
+#pragma unroll
+      for (int i = 1; i < 8; ++i) {
+        s += v[i + 14] - v[i - 1];
+        o[i] = s;
+      }
+      if (c < 4) load_plane(c + 1);   // in flight across the barrier and the horizontal pass
+    }
+    __syncthreads();
+    {
+      const float* rowp = vt + (warp * kFiGC) * 33 + lane;
+      float t[kFiGC + 14];
+#pragma unroll
+      for (int j = 0; j < kFiGC + 14; ++j) t[j] = rowp[j * 33];
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 15; ++j) s += t[j];
+      sums[c][0] = s;
+#pragma unroll
+      for (int i = 1; i < kFiGC; ++i) {
+        s += t[i + 14] - t[i - 1];
+        sums[c][i] = s;
+      }
+    }
+    // Vt[c&1] is next written for plane c+2, after the barrier of plane c+1: safe.
+  }
+
+  const float inv_area = 1.f / 225.f;
+#pragma unroll
+  for (int i = 0; i < kFiGC; ++i) {
+    const float g11 = sums[0][i] * inv_area, g12 = sums[1][i] * inv_area, g22 = sums[2][i] * inv_area;
+    const float h1 = sums[3][i] * inv_area, h2 = sums[4][i] * inv_area;
+    const float w12 = g12 * g12;
+    const float det = fmaf(g11, g22, -w12) + fmaf(-g12, g12, w12);
+    const float idet = 1.f / (det + 1e-3f);
+    const float t1 = g12 * h1;
+    const float nx = fmaf(g11, h2, -t1) + fmaf(-g12, h1, t1);
+    const float t2 = g12 * h2;
+    const float ny = fmaf(g22, h1, -t2) + fmaf(-g12, h2, t2);
+    fl[lane * kFiFlStride + warp * kFiGC + i] = make_float2(nx * idet, ny * idet);
+  }
+  __syncthreads();
+
+  // global phase: consecutive threads along x
+  const float* R0 = R + (size_t)pair * 5 * n;
+  const float* R1 = R0 + 5 * n;
+#pragma unroll 2
+  for (int i = 0; i < (kFiTW * kFiTH) / kFiThreads; ++i) {
+    const int p = tid + i * kFiThreads;
+    const int ty = p / kFiTW, tx = p - ty * kFiTW;
+    const int x = ox0 + tx, y = oy0 + ty;
+    if (x < w && y < h) {
+      const float2 f = fl[ty * kFiFlStride + tx];
+      if (UPDATE) {
+        float mm[5];
+        update_matrices_px(R0, R1, n, w, h, x, y, f.x, f.y, mm);
+        float* Mo = Mout + (size_t)pair * 5 * n + (size_t)y * w + x;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) Mo[c * n] = mm[c];
+      } else {
+        reinterpret_cast<float2*>(flow_out.p[blockIdx.z])[(size_t)y * w + x] = f;
+      }
+    }
+  }
 }
 
 }  // namespace stb
@@ -772,10 +958,17 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
       // frames [fa, fb) still need I_k and R_k
       const int fa = frames_done, fb = p1 + 1;
       if (fb > fa) {
-        const size_t pyr_smem = (size_t)pp.max_rows * kPyrTW * sizeof(float);
-        stb_launch(pyr_kernel, dim3(ceil_div(w, kPyrTW), ceil_div(hh, kPyrTH), fb - fa), dim3(kPyrThreads), pyr_smem, s,
-                   (const uint8_t*)h->gray, h->I, pp, fa);
-        STB_CHECK_LAUNCH("pyr_kernel");
+        if (k == 0) {
+          // rows of the gray plane and of I are 4/16-byte aligned iff W % 4 == 0 (bases are 256-byte aligned)
+          stb_launch(pyr0_kernel, dim3(ceil_div(w, 128), ceil_div(hh, 32), fb - fa), dim3(256), 0, s,
+                     (const uint8_t*)h->gray, h->I, w, hh, pp.taps[0], pp.taps[1], pp.taps[2], fa, (w % 4 == 0) ? 1 : 0);
+          STB_CHECK_LAUNCH("pyr0_kernel");
+        } else {
+          const size_t pyr_smem = (size_t)pp.max_rows * kPyrTW * sizeof(float);
+          stb_launch(pyr_kernel, dim3(ceil_div(w, kPyrTW), ceil_div(hh, kPyrTH), fb - fa), dim3(kPyrThreads), pyr_smem, s,
+                     (const uint8_t*)h->gray, h->I, pp, fa);
+          STB_CHECK_LAUNCH("pyr_kernel");
+        }
         stb_launch(polyexp_kernel, dim3(ceil_div(w, kPeTW), ceil_div(hh, kPeTH), fb - fa), dim3(kPeThreads), 0, s,
                    (const float*)h->I, h->R, w, hh, h->pc, fa);
         STB_CHECK_LAUNCH("polyexp_kernel");
@@ -798,13 +991,19 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
       for (int i = 0; i < np; ++i)
         fo.p[i] = (k == 0) ? d_flow[p0 + i] : h->flow[fl_cur] + (size_t)(p0 + i) * nk * 2;
       int mc = 0;
-      const dim3 grid(ceil_div(w, kItTW), ceil_div(hh, kItTH), np);
+      const bool fast15 = (m == kFiM);
+      const dim3 grid = fast15 ? dim3(ceil_div(w, kFiTW), ceil_div(hh, kFiTH), np)
+                               : dim3(ceil_div(w, kItTW), ceil_div(hh, kItTH), np);
       const bool prof = h->profile && k == 0 && h->prm.num_iters > 1;
       for (int it = 0; it < h->prm.num_iters; ++it) {
         if (it < h->prm.num_iters - 1) {
           if (prof && it == 0) { int prc = prof_mark(h, s); if (prc) return prc; }
-          stb_launch(iter_kernel<true>, grid, dim3(kItThreads), it_smem, s, (const float*)h->M[mc], h->M[mc ^ 1],
-                     (const float*)h->R, fo, w, hh, m, p0);
+          if (fast15)
+            stb_launch(iter15_kernel<true>, grid, dim3(kFiThreads), 0, s, (const float*)h->M[mc], h->M[mc ^ 1],
+                       (const float*)h->R, fo, w, hh, p0);
+          else
+            stb_launch(iter_kernel<true>, grid, dim3(kItThreads), it_smem, s, (const float*)h->M[mc], h->M[mc ^ 1],
+                       (const float*)h->R, fo, w, hh, m, p0);
           mc ^= 1;
           if (prof && it == h->prm.num_iters - 2) {
             int prc = prof_mark(h, s);
@@ -812,8 +1011,12 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
             h->prof_launches += h->prm.num_iters - 1;
           }
         } else {
-          stb_launch(iter_kernel<false>, grid, dim3(kItThreads), it_smem, s, (const float*)h->M[mc], (float*)nullptr,
-                     (const float*)h->R, fo, w, hh, m, p0);
+          if (fast15)
+            stb_launch(iter15_kernel<false>, grid, dim3(kFiThreads), 0, s, (const float*)h->M[mc], (float*)nullptr,
+                       (const float*)h->R, fo, w, hh, p0);
+          else
+            stb_launch(iter_kernel<false>, grid, dim3(kItThreads), it_smem, s, (const float*)h->M[mc], (float*)nullptr,
+                       (const float*)h->R, fo, w, hh, m, p0);
         }
         STB_CHECK_LAUNCH("iter_kernel");
       }

@@ -371,6 +371,16 @@ int stb_hist_rgb16(const uint8_t* const* d_frames, int n, int width, int height,
   }
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned long long nbytes = 3ull * (unsigned long long)width * (unsigned long long)height;
+  for (int i = 0; i < n; ++i)
+    if (!d_frames[i]) { set_error("stb_hist_rgb16: frame %d is NULL", i); return STB_ERR_INVALID; }
+  if (n > kMaxPtrBatch) {
+    // frames carved out of one buffer at a constant stride (a decoder batch / block buffer) need no
+    // pointer table at all: one launch covers the whole batch
+    const ptrdiff_t stride = d_frames[1] - d_frames[0];
+    bool uniform = stride > 0 && (unsigned long long)stride >= nbytes;
+    for (int i = 2; uniform && i < n; ++i) uniform = (d_frames[i] - d_frames[i - 1]) == stride;
+    if (uniform) return stb_hist_rgb16_strided(d_frames[0], (size_t)stride, n, width, height, d_out, stream);
+  }
   STB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)n * STB_HIST_INTS * sizeof(int32_t), s));
   for (int base = 0; base < n; base += kMaxPtrBatch) {
     const int m = n - base < kMaxPtrBatch ? n - base : kMaxPtrBatch;
