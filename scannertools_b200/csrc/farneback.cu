@@ -12,7 +12,7 @@
 //     kernel (separable Gaussian evaluated only at the columns/rows the bilinear
 //     down-sampler needs), no intermediate full-resolution blurred image exists;
 //   * one fused kernel per displacement-update iteration: 15x15 box sums of the 5 M planes
-//     through shared memory (sliding sums, restarted every 8 outputs) -> 2x2 solve -> new
+//     (pairwise-doubling window sums, no subtract recurrence) -> 2x2 solve -> new
 //     flow -> bilinear gather of R1 -> next M, so M is read once and written once per
 //     iteration and the flow of inner iterations never touches HBM;
 //   * frames are processed level-major in pair chunks sized so that one chunk's working set
@@ -175,6 +175,80 @@ pyr_kernel(const uint8_t* __restrict__ gray, float* __restrict__ I, PyrParams p,
 }
 
 // ---------------------------------------------------------------------------------------------
+// pyramid levels 1..3 when the level size is exactly (W / 2^K, H / 2^K) -- the common case
+// (1080p, 720p, 640x480 ...).  cv::resize's bilinear taps are then exactly (0.5, 0.5) at source
+// offset S*o + S/2 - 1, so Gaussian + down-sampling collapse into ONE separable FIR of
+// 2r+2 merged taps c[t] = (g[t] + g[t-1]) / 2 evaluated at stride S = 2^K.
+// Tile = 32 x 8 outputs.  The u8 source region is staged in shared memory with aligned 4-byte
+// loads (interior tiles) or per-byte REFLECT_101 (tiles touching the left/right image edge);
+// phase 1 = horizontal FIR at the 32 output columns for every staged row, phase 2 = vertical FIR.
+// ---------------------------------------------------------------------------------------------
+struct MergedTaps { float c[kMaxGaussTaps + 1]; };
+
+template <int K>
+__global__ void __launch_bounds__(256)
+pyr_pow2_kernel(const uint8_t* __restrict__ gray, float* __restrict__ I, int W, int H, MergedTaps mt, int frame0) {
+  constexpr int S = 1 << K;
+  constexpr int RAD = (K == 1) ? 1 : (K == 2 ? 4 : 9);
+  constexpr int NT = 2 * RAD + 2;
+  constexpr int NROWS = NT + S * 7;
+  constexpr int LEAD = 8 - (RAD + 1 - S / 2);                 // byte offset of the first tap inside the aligned region
+  constexpr int PITCH = ((LEAD + NT + S * 31) + 3) & ~3;      // bytes per staged row
+  __shared__ __align__(16) uint8_t g8[NROWS * PITCH];
+  __shared__ float hx[NROWS][32];
+  __shared__ float taps[NT];
+
+  const int tid = threadIdx.x;
+  const int w = W >> K, h = H >> K;
+  const int frame = frame0 + blockIdx.z;
+  const uint8_t* G = gray + (size_t)frame * W * H;
+  float* out = I + (size_t)frame * w * h;
+  const int ox0 = blockIdx.x * 32, oy0 = blockIdx.y * 8;
+  const int a_lo = S * ox0 - 8;                                // aligned first staged column
+  const int r_lo = S * oy0 + S / 2 - 1 - RAD;                  // first staged row
+  if (tid < NT) taps[tid] = mt.c[tid];
+
+  const bool interior_x = (a_lo >= 0) && (a_lo + PITCH <= W) && ((W & 3) == 0);
+  if (interior_x) {
+    constexpr int WPR = PITCH / 4;
+    for (int idx = tid; idx < NROWS * WPR; idx += 256) {
+      const int rr = idx / WPR, wc = idx - rr * WPR;
+      const int y = reflect101(r_lo + rr, H);
+      reinterpret_cast<unsigned*>(g8)[idx] = __ldg(reinterpret_cast<const unsigned*>(G + (size_t)y * W + a_lo) + wc);
+    }
+  } else {
+    for (int idx = tid; idx < NROWS * PITCH; idx += 256) {
+      const int rr = idx / PITCH, bc = idx - rr * PITCH;
+      const int y = reflect101(r_lo + rr, H);
+      g8[idx] = __ldg(G + (size_t)y * W + reflect101(a_lo + bc, W));
+    }
+  }
+  __syncthreads();
+  {
+    const int ox = tid & 31;
+    const uint8_t* base = g8 + LEAD + S * ox;
+    for (int rr = tid >> 5; rr < NROWS; rr += 8) {
+      const uint8_t* row = base + rr * PITCH;
+      float a = 0.f;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) a = fmaf(taps[t], (float)row[t], a);
+      hx[rr][ox] = a;
+    }
+  }
+  __syncthreads();
+  {
+    const int ox = tid & 31, oyl = tid >> 5;
+    const int x = ox0 + ox, y = oy0 + oyl;
+    if (x < w && y < h) {
+      float a = 0.f;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) a = fmaf(taps[t], hx[S * oyl + t][ox], a);
+      out[(size_t)y * w + x] = a;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // level 0 of the pyramid: 3x3 separable Gaussian (taps t0,t1,t2; REFLECT_101), no resize.
 // Each thread produces a 4 (x) by 4 (y) patch: 6 source rows x (one aligned 4-byte load + the
 // two neighbouring bytes), horizontal blur per row, vertical combine, float4 stores.
@@ -228,73 +302,137 @@ pyr0_kernel(const uint8_t* __restrict__ gray, float* __restrict__ I, int W, int 
 
 // ---------------------------------------------------------------------------------------------
 // polynomial expansion (Appendix A.3): separable 11-tap, replicate borders.  I (h x w) ->
-// R (5 planes of h x w).  Tile 32 x 16, 256 threads, two output rows per thread.
+// R (5 planes of h x w).  Tile 64 x 32, 256 threads.
 // ---------------------------------------------------------------------------------------------
-constexpr int kPeTW = 32, kPeTH = 16, kPeThreads = 256;
-constexpr int kPeInW = kPeTW + 2 * kPolyN;  // 42
-constexpr int kPeInH = kPeTH + 2 * kPolyN;  // 26
+constexpr int kPeTW = 64, kPeTH = 32, kPeThreads = 256;
+constexpr int kPeCols = kPeTW + 2 * kPolyN;   // 74 columns of vertical results per tile
+constexpr int kPeStride = 80;                 // row stride (floats) of the shared arrays; col j <-> x = ox0 - 8 + j
+constexpr int kPeRows = 8 + 2 * kPolyN;       // 18 input rows per vertical item (8 output rows)
 
-__global__ void __launch_bounds__(kPeThreads)
+// Vertical pass: item = (column, group of 8 rows); the 18 input rows come straight from global
+// memory (coalesced along x, replicate clamp), results r0,r1,r2 go to shared memory row-major.
+// Horizontal pass: item = (row, 4 adjacent columns): 16-byte shared loads of a 20-float window
+// per component, 11-tap sums in registers, float4 stores of the 5 output planes.
+__global__ void __launch_bounds__(kPeThreads, 3)
 polyexp_kernel(const float* __restrict__ I, float* __restrict__ R, int w, int h, PolyConsts c, int frame0) {
-  __shared__ float in[kPeInH][kPeInW + 1];
-  __shared__ float v0[kPeTH][kPeInW + 1], v1[kPeTH][kPeInW + 1], v2[kPeTH][kPeInW + 1];
+  __shared__ __align__(16) float V[3][kPeTH][kPeStride];
   const int tid = threadIdx.x;
   const int frame = frame0 + blockIdx.z;
-  const size_t n = (size_t)w * h;
+  const int n = w * h;
   const float* src = I + (size_t)frame * n;
   float* dst = R + (size_t)frame * 5 * n;
   const int ox0 = blockIdx.x * kPeTW, oy0 = blockIdx.y * kPeTH;
 
-  for (int idx = tid; idx < kPeInH * kPeInW; idx += kPeThreads) {
-    const int yy = idx / kPeInW, xx = idx - yy * kPeInW;
-    const int y = min(max(oy0 + yy - kPolyN, 0), h - 1);
-    const int x = min(max(ox0 + xx - kPolyN, 0), w - 1);
-    in[yy][xx] = __ldg(src + (size_t)y * w + x);
-  }
-  __syncthreads();
-  for (int idx = tid; idx < kPeTH * kPeInW; idx += kPeThreads) {
-    const int ty = idx / kPeInW, xx = idx - ty * kPeInW;
-    const float s0 = in[ty + kPolyN][xx];
-    float r0 = s0 * c.g[0], r1 = 0.f, r2 = 0.f;
+  for (int item = tid; item < kPeCols * (kPeTH / 8); item += kPeThreads) {
+    const int g = item / kPeCols, cx = item - g * kPeCols;
+    const int x = min(max(ox0 + cx - kPolyN, 0), w - 1);
+    const int y_first = oy0 + g * 8 - kPolyN;
+    float v[kPeRows];
+    if (y_first >= 0 && y_first + kPeRows - 1 <= h - 1) {
+      const float* p = src + y_first * w + x;
 #pragma unroll
-    for (int k = 1; k <= kPolyN; ++k) {
-      const float a = in[ty + kPolyN - k][xx], b = in[ty + kPolyN + k][xx];
-      const float pp = a + b;
-      r0 = fmaf(c.g[k], pp, r0);
-      r1 = fmaf(c.xg[k], b - a, r1);
-      r2 = fmaf(c.xxg[k], pp, r2);
+      for (int j = 0; j < kPeRows; ++j) v[j] = __ldg(p + j * w);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kPeRows; ++j) v[j] = __ldg(src + min(max(y_first + j, 0), h - 1) * w + x);
     }
-    v0[ty][xx] = r0; v1[ty][xx] = r1; v2[ty][xx] = r2;
+    const int col = cx + 3;   // x = ox0 - 5 + cx  <->  j = cx + 3
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float s0 = v[i + kPolyN];
+      float r0 = s0 * c.g[0], r1 = 0.f, r2 = 0.f;
+#pragma unroll
+      for (int k = 1; k <= kPolyN; ++k) {
+        const float a = v[i + kPolyN - k], b = v[i + kPolyN + k];
+        const float pp = a + b;
+        r0 = fmaf(c.g[k], pp, r0);
+        r1 = fmaf(c.xg[k], b - a, r1);
+        r2 = fmaf(c.xxg[k], pp, r2);
+      }
+      V[0][g * 8 + i][col] = r0;
+      V[1][g * 8 + i][col] = r1;
+      V[2][g * 8 + i][col] = r2;
+    }
   }
   __syncthreads();
-  const int tx = tid & 31;
-  const int x = ox0 + tx;
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const int ty = (tid >> 5) + half * 8;
-    const int y = oy0 + ty;
+
+  const bool vec_ok = (w & 3) == 0;
+  for (int item = tid; item < (kPeTW / 4) * kPeTH; item += kPeThreads) {
+    const int ty = item / (kPeTW / 4), q = item - ty * (kPeTW / 4);
+    const int x = ox0 + q * 4, y = oy0 + ty;
     if (x >= w || y >= h) continue;
-    const int cx = tx + kPolyN;
-    float b1 = v0[ty][cx] * c.g[0], b2 = 0.f, b3 = v1[ty][cx] * c.g[0], b4 = 0.f, b5 = v2[ty][cx] * c.g[0], b6 = 0.f;
+    // window: shared columns [4q, 4q+20)  <->  x-8 .. x+11; pixel i, tap offset d -> index 8 + i + d
+    float b1[4], b2[4], b3[4], b4[4], b5[4], b6[4];
+    {
+      float t[20];
+      const float4* wp = reinterpret_cast<const float4*>(&V[0][ty][q * 4]);
 #pragma unroll
-    for (int k = 1; k <= kPolyN; ++k) {
-      const float p0 = v0[ty][cx + k], m0 = v0[ty][cx - k];
-      const float p1 = v1[ty][cx + k], m1 = v1[ty][cx - k];
-      const float p2 = v2[ty][cx + k], m2 = v2[ty][cx - k];
-      const float tg = p0 + m0;
-      b1 = fmaf(tg, c.g[k], b1);
-      b4 = fmaf(tg, c.xxg[k], b4);
-      b2 = fmaf(p0 - m0, c.xg[k], b2);
-      b3 = fmaf(p1 + m1, c.g[k], b3);
-      b6 = fmaf(p1 - m1, c.xg[k], b6);
-      b5 = fmaf(p2 + m2, c.g[k], b5);
+      for (int j = 0; j < 5; ++j) { const float4 f = wp[j]; t[4 * j] = f.x; t[4 * j + 1] = f.y; t[4 * j + 2] = f.z; t[4 * j + 3] = f.w; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float a1 = t[8 + i] * c.g[0], a2 = 0.f, a4 = 0.f;
+#pragma unroll
+        for (int k = 1; k <= kPolyN; ++k) {
+          const float pl = t[8 + i + k], mi = t[8 + i - k];
+          const float tg = pl + mi;
+          a1 = fmaf(tg, c.g[k], a1);
+          a4 = fmaf(tg, c.xxg[k], a4);
+          a2 = fmaf(pl - mi, c.xg[k], a2);
+        }
+        b1[i] = a1; b2[i] = a2; b4[i] = a4;
+      }
     }
-    const size_t o = (size_t)y * w + x;
-    dst[o] = b3 * c.ig11;                          // d/dy
-    dst[n + o] = b2 * c.ig11;                      // d/dx
-    dst[2 * n + o] = fmaf(b1, c.ig03, b5 * c.ig33);  // yy
-    dst[3 * n + o] = fmaf(b1, c.ig03, b4 * c.ig33);  // xx
-    dst[4 * n + o] = b6 * c.ig55;                  // xy
+    {
+      float t[20];
+      const float4* wp = reinterpret_cast<const float4*>(&V[1][ty][q * 4]);
+#pragma unroll
+      for (int j = 0; j < 5; ++j) { const float4 f = wp[j]; t[4 * j] = f.x; t[4 * j + 1] = f.y; t[4 * j + 2] = f.z; t[4 * j + 3] = f.w; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float a3 = t[8 + i] * c.g[0], a6 = 0.f;
+#pragma unroll
+        for (int k = 1; k <= kPolyN; ++k) {
+          const float pl = t[8 + i + k], mi = t[8 + i - k];
+          a3 = fmaf(pl + mi, c.g[k], a3);
+          a6 = fmaf(pl - mi, c.xg[k], a6);
+        }
+        b3[i] = a3; b6[i] = a6;
+      }
+    }
+    {
+      float t[20];
+      const float4* wp = reinterpret_cast<const float4*>(&V[2][ty][q * 4]);
+#pragma unroll
+      for (int j = 0; j < 5; ++j) { const float4 f = wp[j]; t[4 * j] = f.x; t[4 * j + 1] = f.y; t[4 * j + 2] = f.z; t[4 * j + 3] = f.w; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float a5 = t[8 + i] * c.g[0];
+#pragma unroll
+        for (int k = 1; k <= kPolyN; ++k) a5 = fmaf(t[8 + i + k] + t[8 + i - k], c.g[k], a5);
+        b5[i] = a5;
+      }
+    }
+    float o0[4], o1[4], o2[4], o3[4], o4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      o0[i] = b3[i] * c.ig11;                          // d/dy
+      o1[i] = b2[i] * c.ig11;                          // d/dx
+      o2[i] = fmaf(b1[i], c.ig03, b5[i] * c.ig33);     // yy
+      o3[i] = fmaf(b1[i], c.ig03, b4[i] * c.ig33);     // xx
+      o4[i] = b6[i] * c.ig55;                          // xy
+    }
+    float* d0 = dst + y * w + x;
+    if (vec_ok && x + 3 < w) {
+      *reinterpret_cast<float4*>(d0) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+      *reinterpret_cast<float4*>(d0 + n) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+      *reinterpret_cast<float4*>(d0 + 2 * n) = make_float4(o2[0], o2[1], o2[2], o2[3]);
+      *reinterpret_cast<float4*>(d0 + 3 * n) = make_float4(o3[0], o3[1], o3[2], o3[3]);
+      *reinterpret_cast<float4*>(d0 + 4 * n) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (x + i < w) { d0[i] = o0[i]; d0[n + i] = o1[i]; d0[2 * n + i] = o2[i]; d0[3 * n + i] = o3[i]; d0[4 * n + i] = o4[i]; }
+    }
   }
 }
 
@@ -304,9 +442,10 @@ polyexp_kernel(const float* __restrict__ I, float* __restrict__ R, int w, int h,
 __device__ __forceinline__ float border_w(int d) { return d < 2 ? 0.14f : 0.4472f; }
 
 __device__ __forceinline__ void update_matrices_px(const float* __restrict__ R0, const float* __restrict__ R1,
-                                                   size_t n, int w, int h, int x, int y, float dx, float dy,
+                                                   int n, int w, int h, int x, int y, float dx, float dy,
                                                    float m[5]) {
-  const size_t o = (size_t)y * w + x;
+  // n = w*h <= 2^28 (checked at create), so 5*n fits an int: 32-bit offsets throughout
+  const int o = y * w + x;
   float fx = (float)x + dx, fy = (float)y + dy;
   const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
   fx -= (float)x1; fy -= (float)y1;
@@ -315,7 +454,7 @@ __device__ __forceinline__ void update_matrices_px(const float* __restrict__ R0,
               q4 = __ldg(R0 + 4 * n + o);
   if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
     const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-    const float* p = R1 + (size_t)y1 * w + x1;
+    const float* p = R1 + (y1 * w + x1);
 #define STB_BILIN(pl) (a00 * __ldg(p + (pl) * n) + a01 * __ldg(p + (pl) * n + 1) + a10 * __ldg(p + (pl) * n + w) + a11 * __ldg(p + (pl) * n + w + 1))
     r2 = STB_BILIN(0);
     r3 = STB_BILIN(1);
@@ -361,11 +500,23 @@ updmat_init_kernel(const float* __restrict__ R, const float* __restrict__ flow_c
   if (flow_coarse != nullptr) {
     const float2* fc = reinterpret_cast<const float2*>(flow_coarse) + (size_t)pair * wc * hc;
     int sx, sy; float fx, fy;
-    resize_src(x, scale_x, wc, sx, fx);
-    resize_src(y, scale_y, hc, sy, fy);
+    if (scale_x == 0.5) {   // exact halving: (x + 0.5) * 0.5 - 0.5 is exact in float, skip the double path
+      fx = (float)x * 0.5f - 0.25f; sx = __float2int_rd(fx); fx -= (float)sx;
+      if (sx < 0) { sx = 0; fx = 0.f; }
+      if (sx >= wc - 1) { sx = wc - 1; fx = 0.f; }
+    } else {
+      resize_src(x, scale_x, wc, sx, fx);
+    }
+    if (scale_y == 0.5) {
+      fy = (float)y * 0.5f - 0.25f; sy = __float2int_rd(fy); fy -= (float)sy;
+      if (sy < 0) { sy = 0; fy = 0.f; }
+      if (sy >= hc - 1) { sy = hc - 1; fy = 0.f; }
+    } else {
+      resize_src(y, scale_y, hc, sy, fy);
+    }
     const int sx1 = min(sx + 1, wc - 1), sy1 = min(sy + 1, hc - 1);
-    const float2 f00 = __ldg(fc + (size_t)sy * wc + sx), f01 = __ldg(fc + (size_t)sy * wc + sx1);
-    const float2 f10 = __ldg(fc + (size_t)sy1 * wc + sx), f11 = __ldg(fc + (size_t)sy1 * wc + sx1);
+    const float2 f00 = __ldg(fc + (sy * wc + sx)), f01 = __ldg(fc + (sy * wc + sx1));
+    const float2 f10 = __ldg(fc + (sy1 * wc + sx)), f11 = __ldg(fc + (sy1 * wc + sx1));
     const float ax0 = 1.f - fx, ay0 = 1.f - fy;
     const float h0x = f00.x * ax0 + f01.x * fx, h1x = f10.x * ax0 + f11.x * fx;
     const float h0y = f00.y * ax0 + f01.y * fx, h1y = f10.y * ax0 + f11.y * fx;
@@ -373,10 +524,10 @@ updmat_init_kernel(const float* __restrict__ R, const float* __restrict__ flow_c
     dy = (h0y * ay0 + h1y * fy) * flow_mul;
   }
   float m[5];
-  update_matrices_px(R + (size_t)pair * 5 * n, R + (size_t)(pair + 1) * 5 * n, n, w, h, x, y, dx, dy, m);
-  float* Mo = M + (size_t)pair * 5 * n + (size_t)y * w + x;
+  update_matrices_px(R + (size_t)pair * 5 * n, R + (size_t)(pair + 1) * 5 * n, (int)n, w, h, x, y, dx, dy, m);
+  float* Mo = M + (size_t)pair * 5 * n + (y * w + x);
 #pragma unroll
-  for (int c = 0; c < 5; ++c) Mo[c * n] = m[c];
+  for (int c = 0; c < 5; ++c) Mo[c * (int)n] = m[c];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -384,8 +535,9 @@ updmat_init_kernel(const float* __restrict__ R, const float* __restrict__ flow_c
 //   box sums (2m+1)^2 of the 5 planes of M (replicate border) -> 2x2 solve -> flow
 //   -> (UPDATE)  UpdateMatrices with the new flow -> M_out
 //   -> (!UPDATE) flow written out (float2 per pixel, interleaved dx,dy -- the op's layout)
-// Tile 64 x 32, 256 threads.  Per plane: raw tile (+halo) -> shared; vertical sliding sums
-// (restart every 8 rows) -> transposed shared array; horizontal sliding sums by
+// Tile 64 x 32, 256 threads (generic window size; the production winSize = 15 path is
+// iter15_kernel below).  Per plane: raw tile (+halo) -> shared; vertical window sums
+// -> transposed shared array; horizontal window sums by
 // (lane = row, warp = 8-column group) into registers.  After the solve, flow goes through
 // shared memory so the global-memory phase runs with lanes along x (coalesced).
 // ---------------------------------------------------------------------------------------------
@@ -425,12 +577,9 @@ iter_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const float
     for (int item = tid; item < rawW * 4; item += kItThreads) {
       const int g = item / rawW, cx = item - g * rawW;
       const float* col = raw + (g * 8) * rawS + cx;
-      float s = 0.f;
-      for (int j = 0; j < win; ++j) s += col[j * rawS];
-      Vt[cx * 33 + g * 8] = s;
-#pragma unroll
-      for (int i = 1; i < 8; ++i) {
-        s += col[(i + win - 1) * rawS] - col[(i - 1) * rawS];
+      for (int i = 0; i < 8; ++i) {      // direct sums: no add/subtract recurrence (see box15)
+        float s = 0.f;
+        for (int j = 0; j < win; ++j) s += col[(i + j) * rawS];
         Vt[cx * 33 + g * 8 + i] = s;
       }
     }
@@ -438,12 +587,10 @@ iter_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const float
     // horizontal: lane = output row, warp = group of 8 output columns
     {
       const float* rowp = Vt + (warp * 8) * 33 + lane;
-      float s = 0.f;
-      for (int j = 0; j < win; ++j) s += rowp[j * 33];
-      sums[c][0] = s;
 #pragma unroll
-      for (int i = 1; i < 8; ++i) {
-        s += rowp[(i + win - 1) * 33] - rowp[(i - 1) * 33];
+      for (int i = 0; i < 8; ++i) {
+        float s = 0.f;
+        for (int j = 0; j < win; ++j) s += rowp[(i + j) * 33];
         sums[c][i] = s;
       }
     }
@@ -482,7 +629,7 @@ iter_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const float
       const float2 f = fl[ty * (kItTW + 1) + tx];
       if (UPDATE) {
         float mm[5];
-        update_matrices_px(R + (size_t)pair * 5 * n, R + (size_t)(pair + 1) * 5 * n, n, w, h, x, y, f.x, f.y, mm);
+        update_matrices_px(R + (size_t)pair * 5 * n, R + (size_t)(pair + 1) * 5 * n, (int)n, w, h, x, y, f.x, f.y, mm);
         float* Mo = Mout + (size_t)pair * 5 * n + (size_t)y * w + x;
 #pragma unroll
         for (int c = 0; c < 5; ++c) Mo[c * n] = mm[c];
@@ -506,13 +653,30 @@ static inline size_t iter_smem_bytes(int m) {
 // Differences from the generic kernel above:
 //   * no raw tile in shared memory: each thread item (column, 8-row group) pulls its 22 rows
 //     straight from global memory (coalesced along x; the 2.75x re-reads between row groups
-//     hit L1), forms the vertical sliding sums in registers and writes them transposed;
+//     hit L1), forms the vertical 15-sums in registers and writes them transposed;
 //   * the loads of plane c+1 are issued before the barrier and the horizontal pass of plane c,
 //     so global latency overlaps shared-memory work (software pipeline, double-buffered Vt);
 //   * tile 48 x 32 makes every phase fill the 256 threads: vertical 62 cols x 4 groups = 248
 //     items, horizontal 32 rows x 8 groups of 6 columns = 256 items, update 6 pixels/thread;
 //   * one barrier per plane.
 // ---------------------------------------------------------------------------------------------
+// 15-wide running box sums WITHOUT a sliding (add-new/subtract-old) recurrence: after a window
+// has passed over large values, the subtraction leaves their rounding residue in sums that
+// should be ~0 (flat regions next to strong edges), which the 2x2 solve then amplifies --
+// the reason OpenCV keeps these sums in double.  Pairwise doubling (2,4,8 -> 15 = 8+4+2+1)
+// only ever adds, costs 6*N+20 adds for N outputs and keeps float accuracy relative to the
+// window's own magnitude.
+template <int NOUT>
+__device__ __forceinline__ void box15(const float* t /* NOUT+14 */, float* out /* NOUT */) {
+  float p2[NOUT + 12], p4[NOUT + 8];
+#pragma unroll
+  for (int j = 0; j < NOUT + 12; ++j) p2[j] = t[j] + t[j + 1];
+#pragma unroll
+  for (int j = 0; j < NOUT + 8; ++j) p4[j] = p2[j] + p2[j + 2];
+#pragma unroll
+  for (int i = 0; i < NOUT; ++i) out[i] = ((p4[i] + p4[i + 4]) + p4[i + 8]) + (p2[i + 12] + t[i + 14]);
+}
+
 constexpr int kFiTW = 48, kFiTH = 32, kFiThreads = 256, kFiM = 7;
 constexpr int kFiRawW = kFiTW + 2 * kFiM;     // 62
 constexpr int kFiRows = 8 + 2 * kFiM;         // 22 input rows per vertical item
@@ -561,16 +725,11 @@ iter15_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const flo
   for (int c = 0; c < 5; ++c) {
     float* vt = Vt[c & 1];
     if (vact) {
-      float s = 0.f;
-#pragma unroll
-      for (int j = 0; j < 15; ++j) s += v[j];
+      float vs[8];
+      box15<8>(v, vs);
       float* o = vt + vcx * 33 + vg * 8;
-      o[0] = s;
 #pragma unroll
-      for (int i = 1; i < 8; ++i) {
-        s += v[i + 14] - v[i - 1];
-        o[i] = s;
-      }
+      for (int i = 0; i < 8; ++i) o[i] = vs[i];
       if (c < 4) load_plane(c + 1);   // in flight across the barrier and the horizontal pass
     }
     __syncthreads();
@@ -579,15 +738,7 @@ iter15_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const flo
       float t[kFiGC + 14];
 #pragma unroll
       for (int j = 0; j < kFiGC + 14; ++j) t[j] = rowp[j * 33];
-      float s = 0.f;
-#pragma unroll
-      for (int j = 0; j < 15; ++j) s += t[j];
-      sums[c][0] = s;
-#pragma unroll
-      for (int i = 1; i < kFiGC; ++i) {
-        s += t[i + 14] - t[i - 1];
-        sums[c][i] = s;
-      }
+      box15<kFiGC>(t, sums[c]);
     }
     // Vt[c&1] is next written for plane c+2, after the barrier of plane c+1: safe.
   }
@@ -620,10 +771,10 @@ iter15_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const flo
       const float2 f = fl[ty * kFiFlStride + tx];
       if (UPDATE) {
         float mm[5];
-        update_matrices_px(R0, R1, n, w, h, x, y, f.x, f.y, mm);
-        float* Mo = Mout + (size_t)pair * 5 * n + (size_t)y * w + x;
+        update_matrices_px(R0, R1, (int)n, w, h, x, y, f.x, f.y, mm);
+        float* Mo = Mout + (size_t)pair * 5 * n + (y * w + x);
 #pragma unroll
-        for (int c = 0; c < 5; ++c) Mo[c * n] = mm[c];
+        for (int c = 0; c < 5; ++c) Mo[c * (int)n] = mm[c];
       } else {
         reinterpret_cast<float2*>(flow_out.p[blockIdx.z])[(size_t)y * w + x] = f;
       }
@@ -645,6 +796,8 @@ struct stb_farneback {
   int w[8], h[8];
   PolyConsts pc;
   PyrParams pyr[kMaxScales];
+  MergedTaps merged[kMaxScales];
+  int pow2[kMaxScales];
   int chunk[kMaxScales];
   // device workspace
   uint8_t* gray;    // [F][H*W]
@@ -834,6 +987,12 @@ int stb_farneback_create(int width, int height, int max_pairs, const stb_farneba
     q.scale_y = 1. / ((double)q.h / height);
     gaussian_taps(ksize, sigma, q.taps);
     q.max_rows = (int)std::ceil((kPyrTH - 1) * q.scale_y) + 3 + 2 * q.r;
+    // exact power-of-two level (and the radii the specialised kernel is compiled for)
+    const int expect_r = (k == 1) ? 1 : (k == 2 ? 4 : 9);
+    h->pow2[k] = (k >= 1 && k <= 3 && (width % (1 << k)) == 0 && (height % (1 << k)) == 0 &&
+                  q.w == (width >> k) && q.h == (height >> k) && q.r == expect_r) ? 1 : 0;
+    for (int t = 0; t <= ksize; ++t)
+      h->merged[k].c[t] = 0.5f * ((t < ksize ? q.taps[t] : 0.f) + (t > 0 ? q.taps[t - 1] : 0.f));
     // pair chunk whose level-k working set (R0,R1 shared + M,M' + I + flow ~ 23 floats/px) fits in ~half of L2
     const double per_pair = 23.0 * 4.0 * (double)q.w * q.h;
     int c = (int)(64.0 * 1024 * 1024 / per_pair);
@@ -963,6 +1122,12 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
           stb_launch(pyr0_kernel, dim3(ceil_div(w, 128), ceil_div(hh, 32), fb - fa), dim3(256), 0, s,
                      (const uint8_t*)h->gray, h->I, w, hh, pp.taps[0], pp.taps[1], pp.taps[2], fa, (w % 4 == 0) ? 1 : 0);
           STB_CHECK_LAUNCH("pyr0_kernel");
+        } else if (h->pow2[k]) {
+          const dim3 g(ceil_div(w, 32), ceil_div(hh, 8), fb - fa);
+          if (k == 1) stb_launch(pyr_pow2_kernel<1>, g, dim3(256), 0, s, (const uint8_t*)h->gray, h->I, h->W, h->H, h->merged[k], fa);
+          else if (k == 2) stb_launch(pyr_pow2_kernel<2>, g, dim3(256), 0, s, (const uint8_t*)h->gray, h->I, h->W, h->H, h->merged[k], fa);
+          else stb_launch(pyr_pow2_kernel<3>, g, dim3(256), 0, s, (const uint8_t*)h->gray, h->I, h->W, h->H, h->merged[k], fa);
+          STB_CHECK_LAUNCH("pyr_pow2_kernel");
         } else {
           const size_t pyr_smem = (size_t)pp.max_rows * kPyrTW * sizeof(float);
           stb_launch(pyr_kernel, dim3(ceil_div(w, kPyrTW), ceil_div(hh, kPyrTH), fb - fa), dim3(kPyrThreads), pyr_smem, s,

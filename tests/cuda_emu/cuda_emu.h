@@ -41,7 +41,7 @@ static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) {
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __constant__ static
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 
 namespace cuda_emu {
 struct BlockCtx {

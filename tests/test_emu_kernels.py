@@ -89,6 +89,65 @@ def test_emu_farneback_vs_oracle(emu, h, w, pairs):
         assert e.max() < 1e-4   # in practice float32 agreement is ~1e-5 px
 
 
+def test_emu_farneback_pow2_pyramid_all_levels(emu):
+    """320x256 runs 4 scales whose sizes are exact powers of two: covers the merged-tap
+    pyramid kernels for K = 1, 2, 3 stage by stage (I_k against the restatement)."""
+    h, w = 256, 320
+    clip = synth.textured_clip(6, 2, h, w)
+    hd = C.c_void_p()
+    assert emu.stb_farneback_create(w, h, 1, None, C.byref(hd)) == 0
+    out = np.zeros((h, w, 2), np.float32)
+    g0, g1 = restate.gray(clip[0]), restate.gray(clip[1])
+    for k in (3, 2, 1, 0):
+        lw, lh = restate.pyramid_info(w, h)[k]
+        I0 = np.zeros((lh, lw), np.float32)
+        R1 = np.zeros((5, lh, lw), np.float32)
+        emu.stb_farneback_debug_set(hd, k, 0, P(I0), None, None, P(R1), None, None)
+        assert emu.stb_farneback_run(hd, _lib.ptr_table([f.ctypes.data for f in clip]), 1,
+                                     _lib.ptr_table([out.ctypes.data]), None) == 0
+        _, d = restate.farneback(g0, g1, dump_level=k)
+        assert np.abs(I0 - d['I0']).max() < 2e-4, k
+        assert np.abs(R1 - d['R1'].transpose(2, 0, 1)).max() < 1e-4, k
+    emu.stb_farneback_destroy(hd)
+    e = epe(out, restate.farneback(g0, g1))
+    assert e.max() < 1e-4, e.max()
+
+
+def test_emu_farneback_flat_regions_next_to_edges(emu):
+    """Flat background + moving square: window sums that slide over a strong edge must not
+    leave rounding residue in the flat area (the reason OpenCV sums in double; box15 only adds)."""
+    h, w = 120, 160
+    flat = np.full((2, h, w, 3), 90, np.uint8)
+    flat[0, 50:80, 50:80] = 200
+    flat[1, 52:82, 53:83] = 200
+    hd = C.c_void_p()
+    assert emu.stb_farneback_create(w, h, 1, None, C.byref(hd)) == 0
+    out = np.zeros((h, w, 2), np.float32)
+    assert emu.stb_farneback_run(hd, _lib.ptr_table([f.ctypes.data for f in flat]), 1,
+                                 _lib.ptr_table([out.ctypes.data]), None) == 0
+    emu.stb_farneback_destroy(hd)
+    e = epe(out, restate.optical_flow(flat[0], flat[1]))
+    assert e.mean() <= 1e-3 and e.max() <= 1e-2, (e.mean(), e.max())
+
+
+def test_emu_farneback_generic_window(emu):
+    """winSize != 15 takes the generic iteration kernel."""
+    h, w = 96, 128
+    clip = synth.textured_clip(8, 2, h, w)
+    prm = _lib.FarnebackParams(3, 0.5, 0, 9, 2, 5, 1.2, 0)
+    hd = C.c_void_p()
+    assert emu.stb_farneback_create(w, h, 1, C.byref(prm), C.byref(hd)) == 0
+    out = np.zeros((h, w, 2), np.float32)
+    assert emu.stb_farneback_run(hd, _lib.ptr_table([f.ctypes.data for f in clip]), 1,
+                                 _lib.ptr_table([out.ctypes.data]), None) == 0
+    emu.stb_farneback_destroy(hd)
+    ref = restate.farneback(restate.gray(clip[0]), restate.gray(clip[1]), winsize=9, iters=2)
+    e = epe(out, ref)
+    assert e.max() < 1e-4, e.max()
+    bad = _lib.FarnebackParams(3, 0.5, 0, 8, 3, 5, 1.2, 0)     # even window: rejected
+    assert emu.stb_farneback_create(w, h, 1, C.byref(bad), C.byref(hd)) != 0
+
+
 def test_emu_pipe_host_path(emu):
     h, w = 48, 64
     clip = synth.textured_clip(5, 6, h, w)
