@@ -441,17 +441,15 @@ polyexp_kernel(const float* __restrict__ I, float* __restrict__ R, int w, int h,
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float border_w(int d) { return d < 2 ? 0.14f : 0.4472f; }
 
-__device__ __forceinline__ void update_matrices_px(const float* __restrict__ R0, const float* __restrict__ R1,
-                                                   int n, int w, int h, int x, int y, float dx, float dy,
-                                                   float m[5]) {
-  // n = w*h <= 2^28 (checked at create), so 5*n fits an int: 32-bit offsets throughout
-  const int o = y * w + x;
+__device__ __forceinline__ void update_matrices_q(float q0, float q1, float q2, float q3, float q4,
+                                                  const float* __restrict__ R1, int n, int w, int h, int x, int y,
+                                                  float dx, float dy, float m[5]) {
+  // q0..q4 = R0's five planes at (x, y).  n = w*h <= 2^28 (checked at create), so 5*n fits an
+  // int: 32-bit offsets throughout
   float fx = (float)x + dx, fy = (float)y + dy;
   const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
   fx -= (float)x1; fy -= (float)y1;
   float r2, r3, r4, r5, r6;
-  const float q0 = __ldg(R0 + o), q1 = __ldg(R0 + n + o), q2 = __ldg(R0 + 2 * n + o), q3 = __ldg(R0 + 3 * n + o),
-              q4 = __ldg(R0 + 4 * n + o);
   if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
     const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
     const float* p = R1 + (y1 * w + x1);
@@ -487,47 +485,81 @@ __device__ __forceinline__ void update_matrices_px(const float* __restrict__ R0,
   m[4] = r6 * r2 + r5 * r3;
 }
 
-// initial M of a level from the up-sampled coarser flow (Appendix A.4-5)
+__device__ __forceinline__ void update_matrices_px(const float* __restrict__ R0, const float* __restrict__ R1,
+                                                   int n, int w, int h, int x, int y, float dx, float dy,
+                                                   float m[5]) {
+  const int o = y * w + x;
+  update_matrices_q(__ldg(R0 + o), __ldg(R0 + n + o), __ldg(R0 + 2 * n + o), __ldg(R0 + 3 * n + o),
+                    __ldg(R0 + 4 * n + o), R1, n, w, h, x, y, dx, dy, m);
+}
+
+// initial M of a level from the up-sampled coarser flow (Appendix A.4-5).
+// Two horizontally adjacent pixels per thread (8-byte accesses of R0 / M when w is even).
+__device__ __forceinline__ void upsample_axis(int d, double scale, int n_src, int& s, float& f) {
+  if (scale == 0.5) {   // exact halving: (d + 0.5) * 0.5 - 0.5 is exact in float, skip the double path
+    f = (float)d * 0.5f - 0.25f;
+    s = __float2int_rd(f);
+    f -= (float)s;
+    if (s < 0) { s = 0; f = 0.f; }
+    if (s >= n_src - 1) { s = n_src - 1; f = 0.f; }
+  } else {
+    resize_src(d, scale, n_src, s, f);
+  }
+}
+
+__device__ __forceinline__ float2 upsample_flow(const float2* __restrict__ fc, int wc, int hc, int sy, float fy,
+                                                int x, double scale_x, float flow_mul) {
+  int sx; float fx;
+  upsample_axis(x, scale_x, wc, sx, fx);
+  const int sx1 = min(sx + 1, wc - 1), sy1 = min(sy + 1, hc - 1);
+  const float2 f00 = __ldg(fc + (sy * wc + sx)), f01 = __ldg(fc + (sy * wc + sx1));
+  const float2 f10 = __ldg(fc + (sy1 * wc + sx)), f11 = __ldg(fc + (sy1 * wc + sx1));
+  const float ax0 = 1.f - fx, ay0 = 1.f - fy;
+  const float h0x = f00.x * ax0 + f01.x * fx, h1x = f10.x * ax0 + f11.x * fx;
+  const float h0y = f00.y * ax0 + f01.y * fx, h1y = f10.y * ax0 + f11.y * fx;
+  return make_float2((h0x * ay0 + h1x * fy) * flow_mul, (h0y * ay0 + h1y * fy) * flow_mul);
+}
+
 __global__ void __launch_bounds__(256)
 updmat_init_kernel(const float* __restrict__ R, const float* __restrict__ flow_coarse, float* __restrict__ M,
                    int w, int h, int wc, int hc, double scale_x, double scale_y, float flow_mul, int pair0) {
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int x = (blockIdx.x * 32 + (threadIdx.x & 31)) * 2;
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= w || y >= h) return;
   const int pair = pair0 + blockIdx.z;
-  const size_t n = (size_t)w * h;
-  float dx = 0.f, dy = 0.f;
+  const int n = w * h;
+  const bool two = x + 1 < w;
+  float2 da = make_float2(0.f, 0.f), db = make_float2(0.f, 0.f);
   if (flow_coarse != nullptr) {
     const float2* fc = reinterpret_cast<const float2*>(flow_coarse) + (size_t)pair * wc * hc;
-    int sx, sy; float fx, fy;
-    if (scale_x == 0.5) {   // exact halving: (x + 0.5) * 0.5 - 0.5 is exact in float, skip the double path
-      fx = (float)x * 0.5f - 0.25f; sx = __float2int_rd(fx); fx -= (float)sx;
-      if (sx < 0) { sx = 0; fx = 0.f; }
-      if (sx >= wc - 1) { sx = wc - 1; fx = 0.f; }
-    } else {
-      resize_src(x, scale_x, wc, sx, fx);
-    }
-    if (scale_y == 0.5) {
-      fy = (float)y * 0.5f - 0.25f; sy = __float2int_rd(fy); fy -= (float)sy;
-      if (sy < 0) { sy = 0; fy = 0.f; }
-      if (sy >= hc - 1) { sy = hc - 1; fy = 0.f; }
-    } else {
-      resize_src(y, scale_y, hc, sy, fy);
-    }
-    const int sx1 = min(sx + 1, wc - 1), sy1 = min(sy + 1, hc - 1);
-    const float2 f00 = __ldg(fc + (sy * wc + sx)), f01 = __ldg(fc + (sy * wc + sx1));
-    const float2 f10 = __ldg(fc + (sy1 * wc + sx)), f11 = __ldg(fc + (sy1 * wc + sx1));
-    const float ax0 = 1.f - fx, ay0 = 1.f - fy;
-    const float h0x = f00.x * ax0 + f01.x * fx, h1x = f10.x * ax0 + f11.x * fx;
-    const float h0y = f00.y * ax0 + f01.y * fx, h1y = f10.y * ax0 + f11.y * fx;
-    dx = (h0x * ay0 + h1x * fy) * flow_mul;
-    dy = (h0y * ay0 + h1y * fy) * flow_mul;
+    int sy; float fy;
+    upsample_axis(y, scale_y, hc, sy, fy);
+    da = upsample_flow(fc, wc, hc, sy, fy, x, scale_x, flow_mul);
+    if (two) db = upsample_flow(fc, wc, hc, sy, fy, x + 1, scale_x, flow_mul);
   }
-  float m[5];
-  update_matrices_px(R + (size_t)pair * 5 * n, R + (size_t)(pair + 1) * 5 * n, (int)n, w, h, x, y, dx, dy, m);
-  float* Mo = M + (size_t)pair * 5 * n + (y * w + x);
+  const float* R0 = R + (size_t)pair * 5 * n;
+  const float* R1 = R0 + (size_t)5 * n;
+  const int o = y * w + x;
+  float ma[5], mb[5];
+  float* Mo = M + (size_t)pair * 5 * n + o;
+  if (two && (w & 1) == 0) {
+    float2 q[5];
 #pragma unroll
-  for (int c = 0; c < 5; ++c) Mo[c * (int)n] = m[c];
+    for (int c = 0; c < 5; ++c) q[c] = __ldg(reinterpret_cast<const float2*>(R0 + c * n + o));
+    update_matrices_q(q[0].x, q[1].x, q[2].x, q[3].x, q[4].x, R1, n, w, h, x, y, da.x, da.y, ma);
+    update_matrices_q(q[0].y, q[1].y, q[2].y, q[3].y, q[4].y, R1, n, w, h, x + 1, y, db.x, db.y, mb);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) *reinterpret_cast<float2*>(Mo + c * n) = make_float2(ma[c], mb[c]);
+  } else {
+    update_matrices_px(R0, R1, n, w, h, x, y, da.x, da.y, ma);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) Mo[c * n] = ma[c];
+    if (two) {
+      update_matrices_px(R0, R1, n, w, h, x + 1, y, db.x, db.y, mb);
+#pragma unroll
+      for (int c = 0; c < 5; ++c) Mo[c * n + 1] = mb[c];
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -660,21 +692,28 @@ static inline size_t iter_smem_bytes(int m) {
 //     items, horizontal 32 rows x 8 groups of 6 columns = 256 items, update 6 pixels/thread;
 //   * one barrier per plane.
 // ---------------------------------------------------------------------------------------------
-// 15-wide running box sums WITHOUT a sliding (add-new/subtract-old) recurrence: after a window
-// has passed over large values, the subtraction leaves their rounding residue in sums that
-// should be ~0 (flat regions next to strong edges), which the 2x2 solve then amplifies --
-// the reason OpenCV keeps these sums in double.  Pairwise doubling (2,4,8 -> 15 = 8+4+2+1)
-// only ever adds, costs 6*N+20 adds for N outputs and keeps float accuracy relative to the
-// window's own magnitude.
+// 15-wide window sums WITHOUT a sliding (add-new / subtract-old) recurrence: after a window has
+// passed over large values the subtraction leaves their rounding residue in sums that should be
+// ~0 (flat regions next to strong edges), which the 2x2 solve then amplifies -- the reason
+// OpenCV keeps these sums in double.  Instead (van Herk / Gil-Werman for sums): the NOUT+14
+// inputs split into block A = t[0..14] and block B = t[15..]; window i = suffix_A[i] +
+// prefix_B[i+14].  Only additions, 14 + (NOUT-2) + (NOUT-1) of them, and float accuracy
+// relative to the window's own magnitude.
 template <int NOUT>
 __device__ __forceinline__ void box15(const float* t /* NOUT+14 */, float* out /* NOUT */) {
-  float p2[NOUT + 12], p4[NOUT + 8];
+  static_assert(NOUT >= 2 && NOUT <= 15, "two blocks of 15 must cover every window");
+  float suf[15];
+  suf[14] = t[14];
 #pragma unroll
-  for (int j = 0; j < NOUT + 12; ++j) p2[j] = t[j] + t[j + 1];
+  for (int j = 13; j >= 0; --j) suf[j] = suf[j + 1] + t[j];
+  out[0] = suf[0];
+  float pre = t[15];
+  out[1] = suf[1] + pre;
 #pragma unroll
-  for (int j = 0; j < NOUT + 8; ++j) p4[j] = p2[j] + p2[j + 2];
-#pragma unroll
-  for (int i = 0; i < NOUT; ++i) out[i] = ((p4[i] + p4[i + 4]) + p4[i + 8]) + (p2[i + 12] + t[i + 14]);
+  for (int i = 2; i < NOUT; ++i) {
+    pre += t[14 + i];
+    out[i] = suf[i] + pre;
+  }
 }
 
 constexpr int kFiTW = 48, kFiTH = 32, kFiThreads = 256, kFiM = 7;
@@ -685,7 +724,7 @@ constexpr int kFiVtWords = kFiRawW * 33;      // one transposed vertical-sum buf
 constexpr int kFiFlStride = kFiTW + 1;        // float2 row stride of the staged flow (bank spread)
 
 template <bool UPDATE>
-__global__ void __launch_bounds__(kFiThreads, 3)
+__global__ void __launch_bounds__(kFiThreads, 4)
 iter15_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const float* __restrict__ R,
               PtrBatch<float> flow_out, int w, int h, int pair0) {
   __shared__ float Vt[2][kFiVtWords];
@@ -759,24 +798,49 @@ iter15_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const flo
   }
   __syncthreads();
 
-  // global phase: consecutive threads along x
+  // global phase: consecutive threads along x, two adjacent pixels per thread (8-byte accesses
+  // of R0 / M' / flow when rows are 8-byte aligned, i.e. w even)
   const float* R0 = R + (size_t)pair * 5 * n;
   const float* R1 = R0 + 5 * n;
-#pragma unroll 2
-  for (int i = 0; i < (kFiTW * kFiTH) / kFiThreads; ++i) {
-    const int p = tid + i * kFiThreads;
-    const int ty = p / kFiTW, tx = p - ty * kFiTW;
+  const int ni = (int)n;
+  const bool pair_ok = (w & 1) == 0;
+#pragma unroll 1
+  for (int i = 0; i < (kFiTW * kFiTH) / (2 * kFiThreads); ++i) {
+    const int p2 = tid + i * kFiThreads;            // pixel-pair index inside the tile
+    const int ty = p2 / (kFiTW / 2), tx = (p2 - ty * (kFiTW / 2)) * 2;
     const int x = ox0 + tx, y = oy0 + ty;
-    if (x < w && y < h) {
-      const float2 f = fl[ty * kFiFlStride + tx];
-      if (UPDATE) {
-        float mm[5];
-        update_matrices_px(R0, R1, (int)n, w, h, x, y, f.x, f.y, mm);
-        float* Mo = Mout + (size_t)pair * 5 * n + (y * w + x);
+    if (x >= w || y >= h) continue;
+    const float2 fa = fl[ty * kFiFlStride + tx];
+    const float2 fb = fl[ty * kFiFlStride + tx + 1];
+    const bool two = (x + 1 < w);
+    const int o = y * w + x;
+    if (UPDATE) {
+      float ma[5], mb[5];
+      if (two && pair_ok) {
+        float2 q[5];
 #pragma unroll
-        for (int c = 0; c < 5; ++c) Mo[c * (int)n] = mm[c];
+        for (int c = 0; c < 5; ++c) q[c] = __ldg(reinterpret_cast<const float2*>(R0 + c * ni + o));
+        update_matrices_q(q[0].x, q[1].x, q[2].x, q[3].x, q[4].x, R1, ni, w, h, x, y, fa.x, fa.y, ma);
+        update_matrices_q(q[0].y, q[1].y, q[2].y, q[3].y, q[4].y, R1, ni, w, h, x + 1, y, fb.x, fb.y, mb);
       } else {
-        reinterpret_cast<float2*>(flow_out.p[blockIdx.z])[(size_t)y * w + x] = f;
+        update_matrices_px(R0, R1, ni, w, h, x, y, fa.x, fa.y, ma);
+        if (two) update_matrices_px(R0, R1, ni, w, h, x + 1, y, fb.x, fb.y, mb);
+      }
+      float* Mo = Mout + (size_t)pair * 5 * n + o;
+      if (two && pair_ok) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) *reinterpret_cast<float2*>(Mo + c * ni) = make_float2(ma[c], mb[c]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) { Mo[c * ni] = ma[c]; if (two) Mo[c * ni + 1] = mb[c]; }
+      }
+    } else {
+      float2* fo = reinterpret_cast<float2*>(flow_out.p[blockIdx.z]) + o;
+      if (two && pair_ok && ((reinterpret_cast<uintptr_t>(fo) & 15u) == 0)) {
+        *reinterpret_cast<float4*>(fo) = make_float4(fa.x, fa.y, fb.x, fb.y);
+      } else {
+        fo[0] = fa;
+        if (two) fo[1] = fb;
       }
     }
   }
@@ -1140,7 +1204,7 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
         frames_done = fb;
       }
       (void)F;
-      stb_launch(updmat_init_kernel, dim3(ceil_div(w, 32), ceil_div(hh, 8), np), dim3(256), 0, s, (const float*)h->R,
+      stb_launch(updmat_init_kernel, dim3(ceil_div(w, 64), ceil_div(hh, 8), np), dim3(256), 0, s, (const float*)h->R,
                  coarse, h->M[0], w, hh, wc, hc, up_sx, up_sy, (float)(1. / h->prm.pyr_scale), p0);
       STB_CHECK_LAUNCH("updmat_init_kernel");
       if (dbg && h->dbg_pair >= p0 && h->dbg_pair < p1) {

@@ -264,12 +264,12 @@ def test_farneback_content_classes(torch, ops):
     for tag, clip in (('noise', noise), ('square', flat)):
         out = of.execute(dev(torch, clip)).cpu().numpy()[0]
         check_flow(out, o_flow(clip[0], clip[1]), tag)
-    # identical frames: zero flow in the interior (the last row/column take UpdateMatrices'
-    # out-of-range branch, which leaves a non-zero h there in OpenCV too)
+    # identical frames: near-zero flow (not exactly zero: the last row/column take UpdateMatrices'
+    # out-of-range branch, which leaves a non-zero h that the coarse levels spread, in OpenCV too)
     same = np.stack([noise[0], noise[0]])
     out = of.execute(dev(torch, same)).cpu().numpy()[0]
     check_flow(out, o_flow(same[0], same[1]), 'identical')
-    assert not out[:120, :160].any()
+    assert np.abs(out[:120, :160]).max() < 1e-3
     of.close()
 
 
