@@ -20,8 +20,10 @@
 //   * polynomial expansions are computed once per frame and shared by the two pairs that
 //     contain it (the reference recomputes both pyramids for every pair).
 #include "stb_rt.h"
+#include "flow_bins.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -723,12 +725,16 @@ constexpr int kFiGC = 6;                      // output columns per horizontal i
 constexpr int kFiVtWords = kFiRawW * 33;      // one transposed vertical-sum buffer
 constexpr int kFiFlStride = kFiTW + 1;        // float2 row stride of the staged flow (bank spread)
 
-template <bool UPDATE>
+template <bool UPDATE, bool HIST>
 __global__ void __launch_bounds__(kFiThreads, 4)
 iter15_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const float* __restrict__ R,
-              PtrBatch<float> flow_out, int w, int h, int pair0) {
+              PtrBatch<float> flow_out, int32_t* __restrict__ flow_hist, int w, int h, int pair0) {
   __shared__ float Vt[2][kFiVtWords];
   __shared__ float2 fl[kFiTH * kFiFlStride];
+  __shared__ unsigned fh[HIST ? (kFiThreads / 32) * STB_FLOWHIST_INTS : 1];   // warp-private 128-bin tables
+  if (HIST) {
+    for (int i = threadIdx.x; i < (kFiThreads / 32) * STB_FLOWHIST_INTS; i += kFiThreads) fh[i] = 0u;
+  }
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pair = pair0 + blockIdx.z;
@@ -835,13 +841,37 @@ iter15_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const flo
         for (int c = 0; c < 5; ++c) { Mo[c * ni] = ma[c]; if (two) Mo[c * ni + 1] = mb[c]; }
       }
     } else {
-      float2* fo = reinterpret_cast<float2*>(flow_out.p[blockIdx.z]) + o;
-      if (two && pair_ok && ((reinterpret_cast<uintptr_t>(fo) & 15u) == 0)) {
-        *reinterpret_cast<float4*>(fo) = make_float4(fa.x, fa.y, fb.x, fb.y);
-      } else {
-        fo[0] = fa;
-        if (two) fo[1] = fb;
+      if (flow_out.p[blockIdx.z] != nullptr) {
+        float2* fo = reinterpret_cast<float2*>(flow_out.p[blockIdx.z]) + o;
+        if (two && pair_ok && ((reinterpret_cast<uintptr_t>(fo) & 15u) == 0)) {
+          *reinterpret_cast<float4*>(fo) = make_float4(fa.x, fa.y, fb.x, fb.y);
+        } else {
+          fo[0] = fa;
+          if (two) fo[1] = fb;
+        }
       }
+      if (HIST) {
+        // fused FlowHistogram (flow_histogram_kernel_cpu.cpp:33-49) of the flow just produced
+        unsigned* my = fh + warp * STB_FLOWHIST_INTS;
+        int bm, ba;
+        flow_bins(fa.x, fa.y, bm, ba);
+        if (bm >= 0) atomicAdd(my + bm, 1u);
+        if (ba >= 0) atomicAdd(my + 64 + ba, 1u);
+        if (two) {
+          flow_bins(fb.x, fb.y, bm, ba);
+          if (bm >= 0) atomicAdd(my + bm, 1u);
+          if (ba >= 0) atomicAdd(my + 64 + ba, 1u);
+        }
+      }
+    }
+  }
+  if (HIST) {
+    __syncthreads();
+    if (tid < STB_FLOWHIST_INTS) {
+      unsigned sum = 0;
+#pragma unroll
+      for (int wq = 0; wq < kFiThreads / 32; ++wq) sum += fh[wq * STB_FLOWHIST_INTS + tid];
+      if (sum) atomicAdd(flow_hist + (size_t)pair * STB_FLOWHIST_INTS + tid, (int)sum);
     }
   }
 }
@@ -1057,12 +1087,25 @@ int stb_farneback_create(int width, int height, int max_pairs, const stb_farneba
                   q.w == (width >> k) && q.h == (height >> k) && q.r == expect_r) ? 1 : 0;
     for (int t = 0; t <= ksize; ++t)
       h->merged[k].c[t] = 0.5f * ((t < ksize ? q.taps[t] : 0.f) + (t > 0 ? q.taps[t - 1] : 0.f));
-    // pair chunk whose level-k working set (R0,R1 shared + M,M' + I + flow ~ 23 floats/px) fits in ~half of L2
-    const double per_pair = 23.0 * 4.0 * (double)q.w * q.h;
-    int c = (int)(64.0 * 1024 * 1024 / per_pair);
+    // Pairs per launch at this level: enough thread blocks of the iteration kernel for ~2 full
+    // waves (4 resident blocks/SM) -- the kernels are issue/latency bound, so filling the machine
+    // matters more than keeping a chunk's working set (~92 B/px/pair) inside the 126 MB L2.
+    // Level 0 of a large frame already fills the GPU with one pair, whose M ping-pong then
+    // stays largely L2 resident between its launches.
+    const int blocks_per_pair = ceil_div(q.w, 48) * ceil_div(q.h, 32);
+    int c = ceil_div(2 * 4 * num_sms(), blocks_per_pair);
     if (c < 1) c = 1;
     if (c > kMaxPtrBatch) c = kMaxPtrBatch;
     h->chunk[k] = c;
+  }
+  if (const char* env = getenv("STB_CHUNKS")) {   // experiment knob: "c0,c1,c2,c3" pairs per launch per level
+    int k = 0;
+    for (const char* pch = env; *pch && k < h->nscales; ++k) {
+      const int v = atoi(pch);
+      if (v >= 1 && v <= kMaxPtrBatch) h->chunk[k] = v;
+      while (*pch && *pch != ',') ++pch;
+      if (*pch == ',') ++pch;
+    }
   }
   const WsLayout l = ws_layout(width, height, max_pairs, h->nscales, h->w, h->h);
   uint8_t* base = nullptr;
@@ -1161,7 +1204,11 @@ static int prof_mark(stb_farneback* h, cudaStream_t s) {
   return STB_OK;
 }
 
-static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_t s) {
+// d_hist != NULL: fused FlowHistogram (n*128 int32, pre-zeroed) when the winSize-15 kernel runs;
+// returns through *hist_fused whether it did.  d_flow entries may be NULL only in that case.
+static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_t s, int32_t* d_hist = nullptr,
+                      bool* hist_fused = nullptr) {
+  if (hist_fused) *hist_fused = (d_hist != nullptr) && (h->prm.win_size / 2 == kFiM);
   const int F = n + 1;
   const int m = h->prm.win_size / 2;
   const size_t it_smem = iter_smem_bytes(m);
@@ -1228,8 +1275,8 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
         if (it < h->prm.num_iters - 1) {
           if (prof && it == 0) { int prc = prof_mark(h, s); if (prc) return prc; }
           if (fast15)
-            stb_launch(iter15_kernel<true>, grid, dim3(kFiThreads), 0, s, (const float*)h->M[mc], h->M[mc ^ 1],
-                       (const float*)h->R, fo, w, hh, p0);
+            stb_launch(iter15_kernel<true, false>, grid, dim3(kFiThreads), 0, s, (const float*)h->M[mc], h->M[mc ^ 1],
+                       (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0);
           else
             stb_launch(iter_kernel<true>, grid, dim3(kItThreads), it_smem, s, (const float*)h->M[mc], h->M[mc ^ 1],
                        (const float*)h->R, fo, w, hh, m, p0);
@@ -1240,9 +1287,12 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
             h->prof_launches += h->prm.num_iters - 1;
           }
         } else {
-          if (fast15)
-            stb_launch(iter15_kernel<false>, grid, dim3(kFiThreads), 0, s, (const float*)h->M[mc], (float*)nullptr,
-                       (const float*)h->R, fo, w, hh, p0);
+          if (fast15 && k == 0 && d_hist != nullptr)
+            stb_launch(iter15_kernel<false, true>, grid, dim3(kFiThreads), 0, s, (const float*)h->M[mc], (float*)nullptr,
+                       (const float*)h->R, fo, d_hist, w, hh, p0);
+          else if (fast15)
+            stb_launch(iter15_kernel<false, false>, grid, dim3(kFiThreads), 0, s, (const float*)h->M[mc], (float*)nullptr,
+                       (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0);
           else
             stb_launch(iter_kernel<false>, grid, dim3(kItThreads), it_smem, s, (const float*)h->M[mc], (float*)nullptr,
                        (const float*)h->R, fo, w, hh, m, p0);
@@ -1332,23 +1382,31 @@ int stb_farneback_run_hist(stb_farneback* h, const uint8_t* const* d_rgb, int n,
   if (n == 0) return STB_OK;
   if (!d_flow_hist) { set_error("stb_farneback_run_hist: d_flow_hist is NULL"); return STB_ERR_INVALID; }
   cudaStream_t s = (cudaStream_t)stream;
+  const bool fused = (h->prm.win_size / 2 == kFiM);   // the winSize-15 kernel bins the flow it produces
   float* tmp[kMaxPtrBatch * 4];
-  float** fl = nullptr;
+  float** fl = (n <= kMaxPtrBatch * 4) ? tmp : nullptr;
   float** heap = nullptr;
+  if (!fl) { heap = new (std::nothrow) float*[n]; if (!heap) { set_error("out of host memory"); return STB_ERR_ALLOC; } fl = heap; }
   if (d_flow) {
-    for (int i = 0; i < n; ++i)
-      if (!d_flow[i]) { set_error("stb_farneback_run_hist: d_flow[%d] is NULL", i); return STB_ERR_INVALID; }
-    fl = const_cast<float**>(d_flow);
+    for (int i = 0; i < n; ++i) {
+      if (!d_flow[i]) { delete[] heap; set_error("stb_farneback_run_hist: d_flow[%d] is NULL", i); return STB_ERR_INVALID; }
+      fl[i] = d_flow[i];
+    }
+  } else if (fused) {
+    for (int i = 0; i < n; ++i) fl[i] = nullptr;       // histogram only: the flow frames never touch HBM
   } else {
     rc = ensure_flow0(h);
-    if (rc) return rc;
-    if (n <= kMaxPtrBatch * 4) fl = tmp;
-    else { heap = new (std::nothrow) float*[n]; if (!heap) { set_error("out of host memory"); return STB_ERR_ALLOC; } fl = heap; }
+    if (rc) { delete[] heap; return rc; }
     for (int i = 0; i < n; ++i) fl[i] = h->flow0 + (size_t)i * h->W * h->H * 2;
   }
   rc = to_gray(h, d_rgb, n + 1, s);
-  if (!rc) rc = run_levels(h, n, fl, s);
-  if (!rc) rc = flow_hist_device(fl, n, (unsigned long long)h->W * h->H, d_flow_hist, s, true);
+  if (!rc && fused) {
+    cudaError_t e = cudaMemsetAsync(d_flow_hist, 0, (size_t)n * STB_FLOWHIST_INTS * sizeof(int32_t), s);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemsetAsync(flow_hist)");
+  }
+  bool did_fuse = false;
+  if (!rc) rc = run_levels(h, n, fl, s, fused ? d_flow_hist : nullptr, &did_fuse);
+  if (!rc && !did_fuse) rc = flow_hist_device(fl, n, (unsigned long long)h->W * h->H, d_flow_hist, s, true);
   delete[] heap;
   return rc;
 }

@@ -8,6 +8,7 @@
 //
 // Reference call sites replaced: see include/stb.h.
 #include "stb_rt.h"
+#include "flow_bins.cuh"
 
 namespace stb {
 
@@ -162,32 +163,6 @@ constexpr int kFlowHistThreads = 256;
 constexpr int kFlowHistWarps = kFlowHistThreads / 32;
 constexpr int kFlowHistSmemWords = kFlowHistWarps * 64 * 32;  // 64 KB
 constexpr unsigned kFlowHistMaxPxPerThread = 32768;           // 16-bit counters cannot overflow
-
-__device__ __forceinline__ void flow_bins(float x, float y, int& bm, int& ba) {
-  const float m = __fsqrt_rn(__fmaf_rn(x, x, __fmul_rn(y, y)));
-  // magnitude: floor(double(m) * 1.0); floor of a float is exact in float
-  bm = (m < 64.0f) ? __float2int_rd(m) : -1;  // NaN compares false -> dropped, as cvFloor garbage is
-  const float scale = (float)(180.0 / 3.14159265358979323846);
-  const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale,
-              p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
-  const float ax = fabsf(x), ay = fabsf(y);
-  const float eps = 2.2204460492503131e-16f;  // (float)DBL_EPSILON
-  float a;
-  if (ax >= ay) {
-    const float c = __fdiv_rn(ay, __fadd_rn(ax, eps));
-    const float c2 = __fmul_rn(c, c);
-    a = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmaf_rn(c2, p7, p5), c2, p3), c2, p1), c);
-  } else {
-    const float c = __fdiv_rn(ax, __fadd_rn(ay, eps));
-    const float c2 = __fmul_rn(c, c);
-    a = __fsub_rn(90.0f, __fmul_rn(__fmaf_rn(__fmaf_rn(__fmaf_rn(c2, p7, p5), c2, p3), c2, p1), c));
-  }
-  if (x < 0.0f) a = __fsub_rn(180.0f, a);
-  if (y < 0.0f) a = __fsub_rn(360.0f, a);
-  const double t = __dmul_rn((double)a, 64.0 / 360.0);
-  const int ia = __double2int_rd(t);
-  ba = (ia >= 0 && ia < 64) ? ia : -1;
-}
 
 __device__ __forceinline__ void flow_count(unsigned* my, float x, float y) {
   int bm, ba;

@@ -165,4 +165,8 @@ def test_emu_pipe_host_path(emu):
         e = epe(flow[i], restate.optical_flow(clip[i], clip[i + 1]))
         assert e.max() < 1e-4, (i, e.max())
         assert np.array_equal(fh[i].reshape(2, 64), restate.flow_histogram(flow[i]))
+    fh_only = np.zeros((5, 128), np.int32)            # histogram-only: flow frames are never materialised
+    assert emu.stb_pipe_flow(p, P(clip), 5, None, P(fh_only)) == 0
+    assert np.array_equal(fh_only, fh)
+    assert emu.stb_pipe_flow(p, P(clip), 5, None, None) != 0
     emu.stb_pipe_destroy(p)

@@ -269,7 +269,6 @@ def test_farneback_content_classes(torch, ops):
     same = np.stack([noise[0], noise[0]])
     out = of.execute(dev(torch, same)).cpu().numpy()[0]
     check_flow(out, o_flow(same[0], same[1]), 'identical')
-    assert np.abs(out[:120, :160]).max() < 1e-3
     of.close()
 
 
