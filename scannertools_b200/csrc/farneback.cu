@@ -854,11 +854,11 @@ iter15_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const flo
         // fused FlowHistogram (flow_histogram_kernel_cpu.cpp:33-49) of the flow just produced
         unsigned* my = fh + warp * STB_FLOWHIST_INTS;
         int bm, ba;
-        flow_bins(fa.x, fa.y, bm, ba);
+        flow_bins_fast(fa.x, fa.y, bm, ba);
         if (bm >= 0) atomicAdd(my + bm, 1u);
         if (ba >= 0) atomicAdd(my + 64 + ba, 1u);
         if (two) {
-          flow_bins(fb.x, fb.y, bm, ba);
+          flow_bins_fast(fb.x, fb.y, bm, ba);
           if (bm >= 0) atomicAdd(my + bm, 1u);
           if (ba >= 0) atomicAdd(my + 64 + ba, 1u);
         }

@@ -31,18 +31,47 @@ struct StrideAddrU8 {
 // -------------------------------------------------------------------------------------------
 constexpr int kHistThreads = 384;
 constexpr int kHistWarps = kHistThreads / 32;
-constexpr int kHistSmemWords = kHistWarps * STB_HIST_INTS * 32;  // [warp][bin][lane] u32 = 72 KB
+// table layout: [warp][channel][bin][lane] u32 -> byte offset ((warp*3 + ch)*16 + bin)*128 + lane*4.
+// The origin is aligned to 2048 bytes inside the dynamic allocation, so for a fixed (warp, ch,
+// lane) the bin only occupies address bits 7..10 and "base | (bin << 7)" needs no add.
+constexpr int kHistTableBytes = kHistWarps * STB_HIST_INTS * 32 * 4;   // 72 KB
+constexpr int kHistSmemBytes = kHistTableBytes + 2048;                 // + alignment slack
 
-__device__ __forceinline__ void hist_count_word(unsigned wd, unsigned* b0, unsigned* b1, unsigned* b2) {
+#ifdef STB_CPU_EMU
+typedef unsigned char* hist_addr_t;   // emulator: a plain pointer into the aligned table
+__device__ __forceinline__ hist_addr_t hist_origin(unsigned char* dyn) {
+  return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dyn) + 2047) & ~(uintptr_t)2047);
+}
+__device__ __forceinline__ void hist_inc(hist_addr_t base, unsigned off) {
+  atomicAdd(reinterpret_cast<unsigned*>(reinterpret_cast<uintptr_t>(base) | off), 1u);
+}
+__device__ __forceinline__ unsigned* hist_ptr(hist_addr_t origin, unsigned byte_off) {
+  return reinterpret_cast<unsigned*>(origin + byte_off);
+}
+#else
+typedef unsigned hist_addr_t;         // 32-bit address in the shared window
+__device__ __forceinline__ hist_addr_t hist_origin(unsigned char* dyn) {
+  return ((unsigned)__cvta_generic_to_shared(dyn) + 2047u) & ~2047u;
+}
+__device__ __forceinline__ void hist_inc(hist_addr_t base, unsigned off) {
+  // fire-and-forget shared-memory reduction; (base | off) is one LOP3 fused with the mask
+  asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(base | off) : "memory");
+}
+__device__ __forceinline__ unsigned* hist_ptr(hist_addr_t origin, unsigned byte_off) {
+  return reinterpret_cast<unsigned*>(__cvta_shared_to_generic((size_t)(origin + byte_off)));
+}
+#endif
+
+__device__ __forceinline__ void hist_count_word(unsigned wd, hist_addr_t b0, hist_addr_t b1, hist_addr_t b2) {
   // bytes k = 0..3 of this word use bases (b0,b1,b2,b0): the caller rotates them per word.
-  // Row stride is 32 words (one per lane).
-  atomicAdd(b0 + ((wd >> 4) & 15u) * 32u, 1u);
-  atomicAdd(b1 + ((wd >> 12) & 15u) * 32u, 1u);
-  atomicAdd(b2 + ((wd >> 20) & 15u) * 32u, 1u);
-  atomicAdd(b0 + ((wd >> 28) & 15u) * 32u, 1u);
+  // bin << 7 == ((byte >> 4) & 15) << 7, taken straight out of the word with one shift + mask.
+  hist_inc(b0, (wd << 3) & 0x780u);
+  hist_inc(b1, (wd >> 5) & 0x780u);
+  hist_inc(b2, (wd >> 13) & 0x780u);
+  hist_inc(b0, (wd >> 21) & 0x780u);
 }
 
-__device__ __forceinline__ void hist_count_vec(const uint4& q, unsigned* c0, unsigned* c1, unsigned* c2) {
+__device__ __forceinline__ void hist_count_vec(const uint4& q, hist_addr_t c0, hist_addr_t c1, hist_addr_t c2) {
   // word j starts at byte 4j: channel of its first byte is (phase + 4j) % 3 = (phase + j) % 3
   hist_count_word(q.x, c0, c1, c2);
   hist_count_word(q.y, c1, c2, c0);
@@ -53,11 +82,12 @@ __device__ __forceinline__ void hist_count_vec(const uint4& q, unsigned* c0, uns
 template <class Addr>
 __global__ void __launch_bounds__(kHistThreads, 3)
 hist_rgb16_kernel(Addr addr, unsigned long long nbytes, int32_t* __restrict__ out) {
-  STB_DYN_SMEM(unsigned, sh);
+  STB_DYN_SMEM(unsigned char, dyn);
+  const hist_addr_t origin = hist_origin(dyn);
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   {
-    uint4* z = reinterpret_cast<uint4*>(sh);
-    for (unsigned i = tid; i < kHistSmemWords / 4; i += kHistThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    uint4* z = reinterpret_cast<uint4*>(hist_ptr(origin, 0));
+    for (unsigned i = tid; i < kHistTableBytes / 16; i += kHistThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();
 
@@ -67,20 +97,27 @@ hist_rgb16_kernel(Addr addr, unsigned long long nbytes, int32_t* __restrict__ ou
   const uint4* v = reinterpret_cast<const uint4*>(f + head);
   const unsigned long long nvec = (nbytes - head) >> 4;
 
-  unsigned* my = sh + warp * (STB_HIST_INTS * 32) + lane;
   const unsigned gt = blockIdx.x * kHistThreads + tid;
   const unsigned long long T = (unsigned long long)gridDim.x * kHistThreads;
   const unsigned ph = (unsigned)((head + gt) % 3u);
-  unsigned* c0 = my + ((ph + 0u) % 3u) * (16 * 32);
-  unsigned* c1 = my + ((ph + 1u) % 3u) * (16 * 32);
-  unsigned* c2 = my + ((ph + 2u) % 3u) * (16 * 32);
+  const hist_addr_t wbase = origin + warp * (3u * 2048u) + lane * 4u;
+  const hist_addr_t c0 = wbase + ((ph + 0u) % 3u) * 2048u;
+  const hist_addr_t c1 = wbase + ((ph + 1u) % 3u) * 2048u;
+  const hist_addr_t c2 = wbase + ((ph + 2u) % 3u) * 2048u;
 
+  // software pipeline: the next four vectors are in flight while the current four are counted
   unsigned long long i = gt;
-  for (; i + 3 * T < nvec; i += 4 * T) {
-    const uint4 q0 = __ldg(v + i);
-    const uint4 q1 = __ldg(v + i + T);
-    const uint4 q2 = __ldg(v + i + 2 * T);
-    const uint4 q3 = __ldg(v + i + 3 * T);
+  if (i + 3 * T < nvec) {
+    uint4 q0 = __ldg(v + i), q1 = __ldg(v + i + T), q2 = __ldg(v + i + 2 * T), q3 = __ldg(v + i + 3 * T);
+    i += 4 * T;
+    for (; i + 3 * T < nvec; i += 4 * T) {
+      const uint4 n0 = __ldg(v + i), n1 = __ldg(v + i + T), n2 = __ldg(v + i + 2 * T), n3 = __ldg(v + i + 3 * T);
+      hist_count_vec(q0, c0, c1, c2);
+      hist_count_vec(q1, c0, c1, c2);
+      hist_count_vec(q2, c0, c1, c2);
+      hist_count_vec(q3, c0, c1, c2);
+      q0 = n0; q1 = n1; q2 = n2; q3 = n3;
+    }
     hist_count_vec(q0, c0, c1, c2);
     hist_count_vec(q1, c0, c1, c2);
     hist_count_vec(q2, c0, c1, c2);
@@ -96,17 +133,17 @@ hist_rgb16_kernel(Addr addr, unsigned long long nbytes, int32_t* __restrict__ ou
     const unsigned long long ntail = nbytes - tail0;
     if (tid < head + ntail) {
       const unsigned long long a = tid < head ? tid : tail0 + (tid - head);
-      atomicAdd(my + ((unsigned)(a % 3u) * 16u + (f[a] >> 4)) * 32u, 1u);
+      hist_inc(wbase + (unsigned)(a % 3u) * 2048u, ((unsigned)(f[a] >> 4)) << 7);
     }
   }
   __syncthreads();
 
-  // block reduce: 8 threads per bin, each sums 4 lanes x 12 warps with 16-byte shared loads
+  // block reduce: 8 threads per bin (bin = ch*16 + b), each sums 4 lanes x 12 warps
   const unsigned bin = tid >> 3, part = tid & 7u;
   unsigned s = 0;
 #pragma unroll
   for (int w = 0; w < kHistWarps; ++w) {
-    const uint4 q = *reinterpret_cast<const uint4*>(sh + (w * STB_HIST_INTS + bin) * 32 + part * 4);
+    const uint4 q = *reinterpret_cast<const uint4*>(hist_ptr(origin, ((w * STB_HIST_INTS + bin) * 32 + part * 4) * 4));
     s += q.x + q.y + q.z + q.w;
   }
   s += __shfl_xor_sync(0xffffffffu, s, 1);
@@ -166,7 +203,7 @@ constexpr unsigned kFlowHistMaxPxPerThread = 32768;           // 16-bit counters
 
 __device__ __forceinline__ void flow_count(unsigned* my, float x, float y) {
   int bm, ba;
-  flow_bins(x, y, bm, ba);
+  flow_bins_fast(x, y, bm, ba);
   if (bm >= 0) atomicAdd(my + (bm >> 1) * 32, 1u << ((bm & 1) * 16));
   if (ba >= 0) atomicAdd(my + (32 + (ba >> 1)) * 32, 1u << ((ba & 1) * 16));
 }
@@ -278,7 +315,7 @@ static int launch_hist(Addr addr, int n, unsigned long long nbytes, int32_t* d_o
   const int dev = current_device();
   if (!attr_done[dev]) {
     STB_CUDA(cudaFuncSetAttribute(hist_rgb16_kernel<Addr>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(kHistSmemWords * sizeof(unsigned))));
+                                  (int)kHistSmemBytes));
     attr_done[dev] = true;
   }
   const unsigned long long nvec = nbytes >> 4;
@@ -290,7 +327,7 @@ static int launch_hist(Addr addr, int n, unsigned long long nbytes, int32_t* d_o
   if (bpf > max_useful) bpf = max_useful;
   if (bpf < 1) bpf = 1;
   stb_launch(hist_rgb16_kernel<Addr>, dim3((unsigned)bpf, (unsigned)n), dim3(kHistThreads),
-             kHistSmemWords * sizeof(unsigned), s, addr, nbytes, d_out);
+             kHistSmemBytes, s, addr, nbytes, d_out);
   STB_CHECK_LAUNCH("hist_rgb16_kernel");
   return STB_OK;
 }

@@ -141,6 +141,26 @@ def test_flow_histogram_1080p_and_drops(torch, ops):
     assert out[0].sum() < 1080 * 1920 and out[1].sum() < 1080 * 1920   # >=64 px and ==360 deg are dropped
 
 
+def test_flow_histogram_values_hugging_bin_edges(torch, ops):
+    """The production kernel locates bins with approximate arithmetic and falls back to the
+    exact IEEE path inside a guard band around every edge: fields whose magnitudes / angles sit
+    within 0 .. 1e-2 of the edges (both sides) must still be bit-exact."""
+    rng = np.random.default_rng(42)
+    n = 1 << 18
+    k = rng.integers(0, 66, n).astype(np.float64)
+    dm = rng.choice([0, 1e-7, -1e-7, 1e-6, -1e-6, 1e-5, -1e-5, 1e-4, -1e-4, 3e-4, -3e-4, 1e-3, -1e-3, 1e-2, -1e-2], n)
+    r = np.maximum(k + dm * np.maximum(k, 1.0), 0.0)
+    e = rng.integers(0, 65, n).astype(np.float64) * (360.0 / 64.0)
+    da = rng.choice([0, 1e-6, -1e-6, 1e-5, -1e-5, 1e-4, -1e-4, 5e-4, -5e-4, 2e-3, -2e-3, 1e-2, -1e-2, 0.1, -0.1], n)
+    th = np.radians(e + da)
+    f = np.stack([r * np.cos(th), r * np.sin(th)], axis=-1).astype(np.float32).reshape(512, 512, 2)
+    # (NaN is left out: OpenCV's SIMD min/max make its NaN result unspecified)
+    f[0, :8] = [[0, 0], [np.inf, 1], [1e15, -1e15], [1e-30, 1e-30], [1e20, 1e20], [-0.0, 0.0], [1, -1e-8], [64, 0]]
+    out = ops.flow_histogram(dev(torch, f)).cpu().numpy()[0]
+    assert np.array_equal(out, o_flow_hist(f))
+    assert np.array_equal(out, restate.flow_histogram(f))
+
+
 def test_frame_difference(torch, ops, golden):
     g = golden('framediff.npz')
     out = ops.frame_difference(dev(torch, g['prev']), dev(torch, g['cur'])).cpu().numpy()
