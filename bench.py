@@ -242,8 +242,8 @@ def run_ours(args):
     t_dev = ev0.elapsed_time(ev1) * 1e-3
     launches = lib.stb_launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
-    ms_total, nl = C.c_double(), C.c_longlong()
-    _lib.check(lib.stb_farneback_profile_read(of._h, C.byref(ms_total), C.byref(nl)), lib)
+    ms_total, nl, npi = C.c_double(), C.c_longlong(), C.c_longlong()
+    _lib.check(lib.stb_farneback_profile_read(of._h, C.byref(ms_total), C.byref(nl), C.byref(npi)), lib)
     lib.stb_farneback_profile(of._h, 0)
     fh_dev = d_fh.cpu().numpy().copy()
 
@@ -262,12 +262,12 @@ def run_ours(args):
 
     # ---- max over ranks (timing scalars only; no data-path collective)
     times = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device='cuda')
-    stats = torch.tensor([float(launches), ms_total.value, float(nl.value)], dtype=torch.float64, device='cuda')
+    stats = torch.tensor([float(launches), ms_total.value, float(nl.value), float(npi.value)], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
     t_dev, t_e2e = times.tolist()
-    launches_all, ms_iter_all, nl_all = stats.tolist()
+    launches_all, ms_iter_all, nl_all, npi_all = stats.tolist()
 
     extra = {}
     if rank == 0 and world == 1 and not args.no_extra:
@@ -279,7 +279,8 @@ def run_ours(args):
     if rank == 0:
         peak, peak_kind = measured_peaks()
         total_frames = world * args.steps * P
-        iter_bytes = ITER_BYTES_PER_PX * H * W          # one pair per launch at level 0
+        pairs_per_launch = npi_all / nl_all if nl_all else 0.0    # one launch covers a whole batch of pairs
+        iter_bytes = ITER_BYTES_PER_PX * H * W * pairs_per_launch
         avg_iter_s = (ms_iter_all / nl_all) * 1e-3 if nl_all else float('nan')
         achieved = iter_bytes / avg_iter_s / 1e9 if nl_all else None
         value = total_frames / t_dev
@@ -289,10 +290,11 @@ def run_ours(args):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': workload_config(args),
             'hbm_roofline_frac_whole_op': (FLOW1080_BYTES + FLOWHIST1080_BYTES) * value / world / (peak * 1e9),
-            'roofline': {'bound': 'hbm', 'kernel': 'iter_kernel<true> (level-0 fused box-sum/solve/update-matrices)',
+            'roofline': {'bound': 'hbm', 'kernel': 'iter15_kernel<true,false> (level-0 fused box-sum / 2x2 solve / update-matrices iteration)',
                          'achieved': achieved, 'peak': peak, 'peak_kind': peak_kind, 'unit': 'GB/s',
                          'frac': (achieved / peak) if achieved else None,
-                         'bytes_per_launch': iter_bytes, 'avg_launch_us': avg_iter_s * 1e6, 'launches_timed': int(nl_all),
+                         'bytes_per_launch': iter_bytes, 'pairs_per_launch': pairs_per_launch, 'avg_launch_us': avg_iter_s * 1e6,
+                         'launches_timed': int(nl_all),
                          'share_of_step': (ms_iter_all * 1e-3 / world) / t_dev if t_dev else None,
                          'traffic': NCU_TRAFFIC_BYTES},
             'e2e': {'value': total_frames / t_e2e, 'unit': 'frames/s',

@@ -146,11 +146,13 @@ STB_API int stb_farneback_debug_set(stb_farneback* h, int level, int pair, float
  * stb_launch_count: kernels this library has launched in this process (all entry points).
  * stb_farneback_profile: when enabled, every level-0 pair brackets its fused update-iteration
  * kernels (the dominant kernel) with CUDA events on the launching stream;
- * _profile_read synchronises those events and returns their summed duration and the number of
- * kernel launches they cover. */
+ * _profile_read synchronises those events and returns their summed duration, the number of
+ * kernel launches they cover and the number of (pair x iteration) units those launches
+ * processed (one launch handles a whole batch of pairs). */
 STB_API long long stb_launch_count(void);
 STB_API int stb_farneback_profile(stb_farneback* h, int enable);
-STB_API int stb_farneback_profile_read(stb_farneback* h, double* ms_total, long long* launches);
+STB_API int stb_farneback_profile_read(stb_farneback* h, double* ms_total, long long* launches,
+                                       long long* pair_iterations);
 
 /* ---- host-buffer entry points (end-to-end path) ---------------------------------------------
  * The reference's kernels receive device frames from the Scanner engine; when this library is

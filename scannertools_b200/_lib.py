@@ -44,7 +44,7 @@ SIGNATURES = {
     'stb_farneback_debug_set': (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     'stb_launch_count': (C.c_longlong, []),
     'stb_farneback_profile': (C.c_int, [_vp, C.c_int]),
-    'stb_farneback_profile_read': (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    'stb_farneback_profile_read': (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     'stb_pipe_create': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     'stb_pipe_destroy': (C.c_int, [_vp]),
     'stb_pipe_hist': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),

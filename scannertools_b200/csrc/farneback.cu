@@ -15,8 +15,8 @@
 //     (pairwise-doubling window sums, no subtract recurrence) -> 2x2 solve -> new
 //     flow -> bilinear gather of R1 -> next M, so M is read once and written once per
 //     iteration and the flow of inner iterations never touches HBM;
-//   * frames are processed level-major in pair chunks sized so that one chunk's working set
-//     at that level stays resident in the 126 MB L2;
+//   * frames are processed level-major, a whole batch of pairs per launch (grid.z), so every
+//     launch is many waves deep and the small pyramid levels are not launch-bound;
 //   * polynomial expansions are computed once per frame and shared by the two pairs that
 //     contain it (the reference recomputes both pyramids for every pair).
 #include "stb_rt.h"
@@ -909,6 +909,7 @@ struct stb_farneback {
   std::vector<cudaEvent_t> ev_free;
   std::vector<cudaEvent_t> ev_used;   // (begin, end) pairs
   long long prof_launches;
+  long long prof_pair_iters;   // sum over timed launches of the pairs each one processed
 };
 
 namespace stb {
@@ -1087,15 +1088,12 @@ int stb_farneback_create(int width, int height, int max_pairs, const stb_farneba
                   q.w == (width >> k) && q.h == (height >> k) && q.r == expect_r) ? 1 : 0;
     for (int t = 0; t <= ksize; ++t)
       h->merged[k].c[t] = 0.5f * ((t < ksize ? q.taps[t] : 0.f) + (t > 0 ? q.taps[t - 1] : 0.f));
-    // Pairs per launch at this level: enough thread blocks of the iteration kernel for ~2 full
-    // waves (4 resident blocks/SM) -- the kernels are issue/latency bound, so filling the machine
-    // matters more than keeping a chunk's working set (~92 B/px/pair) inside the 126 MB L2.
-    // Level 0 of a large frame already fills the GPU with one pair, whose M ping-pong then
-    // stays largely L2 resident between its launches.
-    const int blocks_per_pair = ceil_div(q.w, 48) * ceil_div(q.h, 32);
-    int c = ceil_div(2 * 4 * num_sms(), blocks_per_pair);
-    if (c < 1) c = 1;
-    if (c > kMaxPtrBatch) c = kMaxPtrBatch;
+    // Pairs per launch: the whole batch (up to the pointer-table size).  Measured on B200 (1080p,
+    // 16-pair batches): 1 pair per level-0 launch 3585 fps, 2 -> 3944, 4 -> 4276, 8 -> 4499.  The
+    // kernels are issue/latency bound, so wave quantisation and launch tails (1360 blocks over
+    // 592 resident slots = 2.3 waves for one 1080p pair) cost more than keeping one pair's
+    // working set (~92 B/px) resident in the 126 MB L2 buys.
+    int c = kMaxPtrBatch;
     h->chunk[k] = c;
   }
   if (const char* env = getenv("STB_CHUNKS")) {   // experiment knob: "c0,c1,c2,c3" pairs per launch per level
@@ -1166,7 +1164,7 @@ int stb_farneback_profile(stb_farneback* h, int enable) {
   return STB_OK;
 }
 
-int stb_farneback_profile_read(stb_farneback* h, double* ms_total, long long* launches) {
+int stb_farneback_profile_read(stb_farneback* h, double* ms_total, long long* launches, long long* pair_iterations) {
   if (!h) { set_error("stb_farneback_profile_read: NULL handle"); return STB_ERR_INVALID; }
   double total = 0;
   for (size_t i = 0; i + 1 < h->ev_used.size(); i += 2) {
@@ -1179,7 +1177,9 @@ int stb_farneback_profile_read(stb_farneback* h, double* ms_total, long long* la
   h->ev_used.clear();
   if (ms_total) *ms_total = total;
   if (launches) *launches = h->prof_launches;
+  if (pair_iterations) *pair_iterations = h->prof_pair_iters;
   h->prof_launches = 0;
+  h->prof_pair_iters = 0;
   return STB_OK;
 }
 
@@ -1285,6 +1285,7 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
             int prc = prof_mark(h, s);
             if (prc) return prc;
             h->prof_launches += h->prm.num_iters - 1;
+            h->prof_pair_iters += (long long)(h->prm.num_iters - 1) * np;
           }
         } else {
           if (fast15 && k == 0 && d_hist != nullptr)

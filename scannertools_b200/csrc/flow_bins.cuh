@@ -36,15 +36,15 @@ __device__ __forceinline__ void flow_bins(float x, float y, int& bm, int& ba) {
 
 // Same result as flow_bins, cheaper on average: the bins are first located with approximate
 // (MUFU) reciprocal / rsqrt arithmetic and no double precision; only values that land within
-// a guard band of a bin edge (far wider than the approximation error: ~1e-6 relative for the
-// magnitude, < 2e-4 degrees for the angle) -- and anything non-finite, zero or huge -- take the
+// a guard band of a bin edge (10x / 7x wider than the approximation error bound: 4e-6 relative
+// for the magnitude, 1.5e-4 bins = 8e-4 degrees for the angle) -- and anything non-finite, zero or huge -- take the
 // exact IEEE path above.  A value outside the guard band cannot change bin, so the histogram is
 // bit-identical to the exact path's (tests compare the two on edge-heavy fields).
 __device__ __forceinline__ void flow_bins_fast(float x, float y, int& bm, int& ba) {
   const float s = __fmaf_rn(x, x, __fmul_rn(y, y));
   const float m = s * rsqrtf(s);
   bool exact = !(s > 1e-30f && s < 1e30f);
-  exact |= fabsf(m - rintf(m)) <= 2e-4f * fmaxf(m, 1.0f) && m < 65.0f;
+  exact |= fabsf(m - rintf(m)) <= 4e-6f * fmaxf(m, 1.0f) && m < 65.0f;   // approximation error <= ~4e-7 relative
   const float scale = (float)(180.0 / 3.14159265358979323846);
   const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale,
               p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
@@ -57,7 +57,7 @@ __device__ __forceinline__ void flow_bins_fast(float x, float y, int& bm, int& b
   if (x < 0.0f) a = 180.0f - a;
   if (y < 0.0f) a = 360.0f - a;
   const float t = a * (64.0f / 360.0f);
-  exact |= fabsf(t - rintf(t)) <= 1e-3f;
+  exact |= fabsf(t - rintf(t)) <= 1.5e-4f;                               // approximation error <= ~2e-5 bins
   if (exact) {
     flow_bins(x, y, bm, ba);
     return;

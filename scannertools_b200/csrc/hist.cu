@@ -322,7 +322,9 @@ static int launch_hist(Addr addr, int n, unsigned long long nbytes, int32_t* d_o
   // one resident wave (3 blocks/SM) spread over the frames of this launch; never more blocks
   // than there are 4-vector iterations of work
   const int wave = num_sms() * 3;
-  long long bpf = (wave + n - 1) / n;
+  // blocks per frame: fill one resident wave without spilling a handful of blocks into a second
+  // one (448 blocks on 444 slots costs ~25%); with more frames than slots, one block per frame.
+  long long bpf = wave / n;
   const long long max_useful = (long long)((nvec + (unsigned long long)kHistThreads * 4 - 1) / ((unsigned long long)kHistThreads * 4));
   if (bpf > max_useful) bpf = max_useful;
   if (bpf < 1) bpf = 1;
@@ -342,7 +344,7 @@ static int launch_flow_hist(Addr addr, int n, unsigned long long npx, int32_t* d
     attr_done[dev] = true;
   }
   const int wave = num_sms() * 3;
-  long long bpf = (wave + n - 1) / n;
+  long long bpf = wave / n;
   const long long max_useful = (long long)((npx / 2 + (unsigned long long)kFlowHistThreads * 2 - 1) / ((unsigned long long)kFlowHistThreads * 2));
   const long long min_needed = (long long)((npx + (unsigned long long)kFlowHistThreads * kFlowHistMaxPxPerThread - 1) /
                                            ((unsigned long long)kFlowHistThreads * kFlowHistMaxPxPerThread));

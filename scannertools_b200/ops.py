@@ -74,6 +74,17 @@ def histogram(frames, stream=None):
     layout `types.histograms` parses).  Bit-exact with the reference (bin = byte >> 4)."""
     torch = _torch()
     lib = _lib.load()
+    if isinstance(frames, torch.Tensor) and frames.dim() == 4 and frames.shape[0] > 0:
+        # one contiguous batch (a decoder batch / block buffer): strided entry point, one launch
+        _require_cuda(frames, torch.uint8, 'frames')
+        n, H, W, c = frames.shape
+        if c != 3:
+            raise ValueError('frames: expected 3 channels, got %d' % c)
+        out = torch.empty((n, 3, HIST_BINS), dtype=torch.int32, device=frames.device)
+        with torch.cuda.device(frames.device):
+            _lib.check(lib.stb_hist_rgb16_strided(C.c_void_p(frames.data_ptr()), H * W * 3, n, W, H,
+                                                  C.c_void_p(out.data_ptr()), _stream_ptr(stream)), lib)
+        return out
     lst, H, W = _frames_list(frames, torch.uint8, 'frames', 3)
     n = len(lst)
     dev = lst[0].device if n else torch.device('cuda')
@@ -112,6 +123,16 @@ def flow_histogram(flows, stream=None):
     magnitude bins then angle bins, the layout `flow_hist_reader` parses)."""
     torch = _torch()
     lib = _lib.load()
+    if isinstance(flows, torch.Tensor) and flows.dim() == 4 and flows.shape[0] > 0:
+        _require_cuda(flows, torch.float32, 'flows')
+        n, H, W, c = flows.shape
+        if c != 2:
+            raise ValueError('flows: expected 2 channels, got %d' % c)
+        out = torch.empty((n, 2, FLOW_HIST_BINS), dtype=torch.int32, device=flows.device)
+        with torch.cuda.device(flows.device):
+            _lib.check(lib.stb_flow_hist_strided(C.c_void_p(flows.data_ptr()), H * W * 8, n, W, H,
+                                                 C.c_void_p(out.data_ptr()), _stream_ptr(stream)), lib)
+        return out
     lst, H, W = _frames_list(flows, torch.float32, 'flows', 2)
     n = len(lst)
     dev = lst[0].device if n else torch.device('cuda')
