@@ -296,7 +296,8 @@ def run_ours(args):
                          'bytes_per_launch': iter_bytes, 'pairs_per_launch': pairs_per_launch, 'avg_launch_us': avg_iter_s * 1e6,
                          'launches_timed': int(nl_all),
                          'share_of_step': (ms_iter_all * 1e-3 / world) / t_dev if t_dev else None,
-                         'traffic': NCU_TRAFFIC_BYTES},
+                         'traffic': NCU_TRAFFIC_BYTES_PER_PAIR * pairs_per_launch,
+                         'traffic_source': 'profiles/r01_ncu_full_table.txt (2-pair capture, scaled per pair)'},
             'e2e': {'value': total_frames / t_e2e, 'unit': 'frames/s',
                     'h2d_bytes_per_step': world * (P + 1) * H * W * 3 - world * (P // B - 1) * H * W * 3 * 0,
                     'd2h_bytes_per_step': world * P * 512, 'ms_per_step': 1e3 * t_e2e / args.steps,
@@ -313,9 +314,10 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one iter_kernel<true> level-0 launch from the
-# committed `ncu --set full` capture (profiles/); None until a capture exists.
-NCU_TRAFFIC_BYTES = None
+# dram__bytes_read.sum + dram__bytes_write.sum of iter15_kernel<true,false> at level 0 from the
+# committed `ncu --set full` capture (profiles/r01_ncu_full_table.txt: grid (40,34,2), 248.1 MB read
+# + 64.5..65.1 MB written for 2 pairs), per PAIR; scaled by the pairs one bench launch processes.
+NCU_TRAFFIC_BYTES_PER_PAIR = 156.4e6
 
 
 def extra_workloads(torch, ops, lib, args):
@@ -404,7 +406,7 @@ def cpu_baseline_child():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--pairs', type=int, default=32, help='frame pairs per step')

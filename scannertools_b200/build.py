@@ -49,5 +49,35 @@ def build(force=False, verbose=False):
     return OUT
 
 
+OPS_OUT = os.path.join(HERE, 'libscannertools_imgproc.so')
+OPS_SOURCES = ['histogram_kernel_gpu.cpp', 'optical_flow_kernel_gpu.cpp', 'flow_histogram_kernel_gpu.cpp',
+               'frame_difference_kernel_gpu.cpp', 'compat_runtime.cpp']
+
+
+def build_scanner_ops(force=False, scanner_include=None):
+    """Builds the Scanner kernel classes (csrc/scanner_ops) into libscannertools_imgproc.so -- the
+    name the reference's `import scannertools.imgproc` registers.  Against the compat shim by
+    default; pass the real Scanner include dir to build the drop-in (then compat_runtime.cpp,
+    the shim's allocator + test harness, is left out)."""
+    lib = build(force=force)
+    nvcc = find_nvcc()
+    cuda_home = os.path.dirname(os.path.dirname(nvcc))
+    ops_dir = os.path.join(CSRC, 'scanner_ops')
+    srcs = [os.path.join(ops_dir, s) for s in OPS_SOURCES if scanner_include is None or s != 'compat_runtime.cpp']
+    deps = srcs + [lib] + [os.path.join(dp, f) for dp, _, fs in os.walk(os.path.join(CSRC, 'scanner_compat')) for f in fs]
+    if not force and not _newer(OPS_OUT, deps):
+        return OPS_OUT
+    inc = scanner_include or os.path.join(CSRC, 'scanner_compat')
+    cmd = ['g++', '-O2', '-std=c++14', '-fPIC', '-shared', '-fvisibility=hidden', '-I', inc, '-I', ops_dir,
+           '-I', os.path.join(ROOT, 'include'), '-I', os.path.join(cuda_home, 'include'), '-o', OPS_OUT] + srcs + [
+           '-L', HERE, '-l:libscannertools_b200.so', '-Wl,-rpath,$ORIGIN',
+           '-L', os.path.join(cuda_home, 'lib64'), '-lcudart']
+    if scanner_include is not None:
+        cmd.insert(1, '-DSTB_SKIP_OP_DECLARATIONS')
+    subprocess.check_call(cmd)
+    return OPS_OUT
+
+
 if __name__ == '__main__':
     print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    print(build_scanner_ops(force='--force' in sys.argv))

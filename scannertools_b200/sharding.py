@@ -21,3 +21,35 @@ def stream_assignment(n_streams, world):
     """C5: whole streams are pinned to GPUs so per-stream previous-frame state never crosses
     devices.  Returns rank -> list of stream ids (round-robin)."""
     return [[s for s in range(n_streams) if s % world == r] for r in range(world)]
+
+
+def gather_frame_outputs(local, n_frames, rank, world, group=None):
+    """Concatenates per-frame outputs (numpy, first axis = this rank's frames, in order) from all
+    ranks on every rank, in frame order.  Host-side plumbing over torch.distributed (gloo or
+    nccl object collectives); the data path itself has no collective -- this is the 'per-frame
+    outputs are concatenated on the host' step."""
+    import numpy as np
+    import torch.distributed as dist
+    if world == 1:
+        return np.asarray(local)
+    parts = [None] * world
+    dist.all_gather_object(parts, np.asarray(local), group=group)
+    out = np.concatenate([p for p in parts if len(p)], axis=0) if any(len(p) for p in parts) else np.asarray(local)
+    assert out.shape[0] == n_frames, (out.shape, n_frames)
+    return out
+
+
+def sharded_shot_detection(frames_of_rank, n_frames, rank, world, histogram_fn, scores_fn, prev_hist=None):
+    """Shot detection over a frame-range-sharded clip.
+
+    frames_of_rank : this rank's frames [f0, f1)
+    histogram_fn   : frames -> int32 [m, 3, 16]     (ops.histogram on the GPU path)
+    scores_fn      : (hist, prev_hist or None) -> int32 [m]   (ops.shot_scores)
+    prev_hist      : histogram of frame f0-1 (from the neighbouring rank); None on rank 0
+    Returns (boundaries, scores[n_frames]) on every rank: the +-500-frame window test spans shard
+    boundaries, so it runs once over the concatenated scores (shot_detection.py:22-26)."""
+    from . import shot_detection
+    hist = histogram_fn(frames_of_rank)
+    scores = scores_fn(hist, prev_hist)
+    all_scores = gather_frame_outputs(scores, n_frames, rank, world)
+    return shot_detection.boundaries_from_scores(all_scores), all_scores

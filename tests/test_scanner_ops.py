@@ -1,0 +1,66 @@
+"""The C++ Scanner kernel classes (scannertools_b200/csrc/scanner_ops), built against the
+Scanner-API compat shim into libscannertools_imgproc.so, driven the way Scanner's evaluator
+drives a kernel: registry lookup by op name, Elements in, execute(), Elements out."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import restate
+from scannertools_b200 import synth
+
+
+@pytest.fixture(scope='module')
+def shim():
+    from scannertools_b200 import build
+    lib = C.CDLL(build.build_scanner_ops())
+    lib.stb_shim_registered.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    return lib
+
+
+def P(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def test_ops_and_kernels_registered_under_reference_names(shim):
+    """REGISTER_OP / REGISTER_KERNEL lines keep the reference's names, batching and stencils
+    (histogram_kernel_gpu.cpp:79-82, optical_flow_kernel_cpu.cpp:51-54, optical_flow_kernel_gpu.cpp:109-112,
+    flow_histogram_kernel_cpu.cpp:62-67, frame_difference_kernel_cpu.cpp:74-80)."""
+    expect = {b'Histogram': (1, 0, 0), b'OpticalFlow': (1, 0, 1), b'FlowHistogram': (1, 0, 0), b'FrameDifference': (0, -1, 0)}
+    for op, (batched, lo, hi) in expect.items():
+        b, l, h = C.c_int(-1), C.c_int(99), C.c_int(99)
+        assert shim.stb_shim_registered(op, C.byref(b), C.byref(l), C.byref(h)) == 1, op
+        assert (b.value, l.value, h.value) == (batched, lo, hi), op
+    assert shim.stb_shim_registered(b'NoSuchOp', None, None, None) == 0
+
+
+@pytest.mark.gpu
+def test_histogram_kernel_class(shim):
+    clip = synth.noise_clip(3, 9, 90, 160)
+    out = np.zeros((9, 48), np.int32)
+    assert shim.stb_shim_histogram(P(clip), 9, 160, 90, P(out), 0) == 0
+    assert np.array_equal(out, np.stack([restate.histogram(f).reshape(-1) for f in clip]))
+
+
+@pytest.mark.gpu
+def test_optical_flow_and_flow_histogram_kernel_classes(shim):
+    h, w = 120, 160
+    clip = synth.textured_clip(2, 4, h, w)
+    flow = np.zeros((3, h, w, 2), np.float32)
+    assert shim.stb_shim_optical_flow(P(clip), 3, w, h, P(flow), 0) == 0
+    for i in range(3):
+        d = flow[i].astype(np.float64) - restate.optical_flow(clip[i], clip[i + 1])
+        e = np.sqrt((d * d).sum(-1))
+        assert e.mean() <= 1e-3 and e.max() <= 1e-2, (i, e.max())
+    fh = np.zeros((3, 128), np.int32)
+    assert shim.stb_shim_flow_histogram(P(flow), 3, w, h, P(fh), 0) == 0
+    for i in range(3):
+        assert np.array_equal(fh[i].reshape(2, 64), restate.flow_histogram(flow[i]))
+
+
+@pytest.mark.gpu
+def test_frame_difference_kernel_class(shim):
+    a = synth.noise_clip(5, 2, 37, 53)
+    out = np.zeros_like(a[0])
+    assert shim.stb_shim_frame_difference(P(a[0]), P(a[1]), 53, 37, 3, P(out), 0) == 0
+    assert np.array_equal(out, restate.frame_difference(a[0], a[1]))
