@@ -61,7 +61,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -409,7 +409,7 @@ def main():
     ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--pairs', type=int, default=32, help='frame pairs per step')
+    ap.add_argument('--pairs', type=int, default=64, help='frame pairs per step')
     ap.add_argument('--batch', type=int, default=16, help='pairs per C-ABI batch call')
     ap.add_argument('--no-extra', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')

@@ -725,6 +725,84 @@ constexpr int kFiGC = 6;                      // output columns per horizontal i
 constexpr int kFiVtWords = kFiRawW * 33;      // one transposed vertical-sum buffer
 constexpr int kFiFlStride = kFiTW + 1;        // float2 row stride of the staged flow (bank spread)
 
+// Global-memory phase shared by both winSize-15 kernels: consecutive threads along x, two adjacent
+// pixels per thread (8-byte accesses of R0 / M' / flow when rows are 8-byte aligned, i.e. w even).
+template <bool UPDATE, bool HIST>
+__device__ __forceinline__ void iter15_global_phase(const float2* fl, unsigned* fh, float* __restrict__ Mout,
+                                                    const float* __restrict__ R, const PtrBatch<float>& flow_out,
+                                                    int32_t* __restrict__ flow_hist, int w, int h, int pair, int ox0, int oy0) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const size_t n = (size_t)w * h;
+  const float* R0 = R + (size_t)pair * 5 * n;
+  const float* R1 = R0 + 5 * n;
+  const int ni = (int)n;
+  const bool pair_ok = (w & 1) == 0;
+#pragma unroll 1
+  for (int i = 0; i < (kFiTW * kFiTH) / (2 * kFiThreads); ++i) {
+    const int p2 = tid + i * kFiThreads;            // pixel-pair index inside the tile
+    const int ty = p2 / (kFiTW / 2), tx = (p2 - ty * (kFiTW / 2)) * 2;
+    const int x = ox0 + tx, y = oy0 + ty;
+    if (x >= w || y >= h) continue;
+    const float2 fa = fl[ty * kFiFlStride + tx];
+    const float2 fb = fl[ty * kFiFlStride + tx + 1];
+    const bool two = (x + 1 < w);
+    const int o = y * w + x;
+    if (UPDATE) {
+      float ma[5], mb[5];
+      if (two && pair_ok) {
+        float2 q[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) q[c] = __ldg(reinterpret_cast<const float2*>(R0 + c * ni + o));
+        update_matrices_q(q[0].x, q[1].x, q[2].x, q[3].x, q[4].x, R1, ni, w, h, x, y, fa.x, fa.y, ma);
+        update_matrices_q(q[0].y, q[1].y, q[2].y, q[3].y, q[4].y, R1, ni, w, h, x + 1, y, fb.x, fb.y, mb);
+      } else {
+        update_matrices_px(R0, R1, ni, w, h, x, y, fa.x, fa.y, ma);
+        if (two) update_matrices_px(R0, R1, ni, w, h, x + 1, y, fb.x, fb.y, mb);
+      }
+      float* Mo = Mout + (size_t)pair * 5 * n + o;
+      if (two && pair_ok) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) *reinterpret_cast<float2*>(Mo + c * ni) = make_float2(ma[c], mb[c]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) { Mo[c * ni] = ma[c]; if (two) Mo[c * ni + 1] = mb[c]; }
+      }
+    } else {
+      if (flow_out.p[blockIdx.z] != nullptr) {
+        float2* fo = reinterpret_cast<float2*>(flow_out.p[blockIdx.z]) + o;
+        if (two && pair_ok && ((reinterpret_cast<uintptr_t>(fo) & 15u) == 0)) {
+          *reinterpret_cast<float4*>(fo) = make_float4(fa.x, fa.y, fb.x, fb.y);
+        } else {
+          fo[0] = fa;
+          if (two) fo[1] = fb;
+        }
+      }
+      if (HIST) {
+        // fused FlowHistogram (flow_histogram_kernel_cpu.cpp:33-49) of the flow just produced
+        unsigned* my = fh + warp * STB_FLOWHIST_INTS;
+        int bm, ba;
+        flow_bins_fast(fa.x, fa.y, bm, ba);
+        if (bm >= 0) atomicAdd(my + bm, 1u);
+        if (ba >= 0) atomicAdd(my + 64 + ba, 1u);
+        if (two) {
+          flow_bins_fast(fb.x, fb.y, bm, ba);
+          if (bm >= 0) atomicAdd(my + bm, 1u);
+          if (ba >= 0) atomicAdd(my + 64 + ba, 1u);
+        }
+      }
+    }
+  }
+  if (HIST) {
+    __syncthreads();
+    if (tid < STB_FLOWHIST_INTS) {
+      unsigned sum = 0;
+#pragma unroll
+      for (int wq = 0; wq < kFiThreads / 32; ++wq) sum += fh[wq * STB_FLOWHIST_INTS + tid];
+      if (sum) atomicAdd(flow_hist + (size_t)pair * STB_FLOWHIST_INTS + tid, (int)sum);
+    }
+  }
+}
+
 template <bool UPDATE, bool HIST>
 __global__ void __launch_bounds__(kFiThreads, 4)
 iter15_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const float* __restrict__ R,
@@ -804,76 +882,172 @@ iter15_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const flo
   }
   __syncthreads();
 
-  // global phase: consecutive threads along x, two adjacent pixels per thread (8-byte accesses
-  // of R0 / M' / flow when rows are 8-byte aligned, i.e. w even)
-  const float* R0 = R + (size_t)pair * 5 * n;
-  const float* R1 = R0 + 5 * n;
-  const int ni = (int)n;
-  const bool pair_ok = (w & 1) == 0;
-#pragma unroll 1
-  for (int i = 0; i < (kFiTW * kFiTH) / (2 * kFiThreads); ++i) {
-    const int p2 = tid + i * kFiThreads;            // pixel-pair index inside the tile
-    const int ty = p2 / (kFiTW / 2), tx = (p2 - ty * (kFiTW / 2)) * 2;
-    const int x = ox0 + tx, y = oy0 + ty;
-    if (x >= w || y >= h) continue;
-    const float2 fa = fl[ty * kFiFlStride + tx];
-    const float2 fb = fl[ty * kFiFlStride + tx + 1];
-    const bool two = (x + 1 < w);
-    const int o = y * w + x;
-    if (UPDATE) {
-      float ma[5], mb[5];
-      if (two && pair_ok) {
-        float2 q[5];
-#pragma unroll
-        for (int c = 0; c < 5; ++c) q[c] = __ldg(reinterpret_cast<const float2*>(R0 + c * ni + o));
-        update_matrices_q(q[0].x, q[1].x, q[2].x, q[3].x, q[4].x, R1, ni, w, h, x, y, fa.x, fa.y, ma);
-        update_matrices_q(q[0].y, q[1].y, q[2].y, q[3].y, q[4].y, R1, ni, w, h, x + 1, y, fb.x, fb.y, mb);
-      } else {
-        update_matrices_px(R0, R1, ni, w, h, x, y, fa.x, fa.y, ma);
-        if (two) update_matrices_px(R0, R1, ni, w, h, x + 1, y, fb.x, fb.y, mb);
-      }
-      float* Mo = Mout + (size_t)pair * 5 * n + o;
-      if (two && pair_ok) {
-#pragma unroll
-        for (int c = 0; c < 5; ++c) *reinterpret_cast<float2*>(Mo + c * ni) = make_float2(ma[c], mb[c]);
-      } else {
-#pragma unroll
-        for (int c = 0; c < 5; ++c) { Mo[c * ni] = ma[c]; if (two) Mo[c * ni + 1] = mb[c]; }
-      }
-    } else {
-      if (flow_out.p[blockIdx.z] != nullptr) {
-        float2* fo = reinterpret_cast<float2*>(flow_out.p[blockIdx.z]) + o;
-        if (two && pair_ok && ((reinterpret_cast<uintptr_t>(fo) & 15u) == 0)) {
-          *reinterpret_cast<float4*>(fo) = make_float4(fa.x, fa.y, fb.x, fb.y);
-        } else {
-          fo[0] = fa;
-          if (two) fo[1] = fb;
-        }
-      }
-      if (HIST) {
-        // fused FlowHistogram (flow_histogram_kernel_cpu.cpp:33-49) of the flow just produced
-        unsigned* my = fh + warp * STB_FLOWHIST_INTS;
-        int bm, ba;
-        flow_bins_fast(fa.x, fa.y, bm, ba);
-        if (bm >= 0) atomicAdd(my + bm, 1u);
-        if (ba >= 0) atomicAdd(my + 64 + ba, 1u);
-        if (two) {
-          flow_bins_fast(fb.x, fb.y, bm, ba);
-          if (bm >= 0) atomicAdd(my + bm, 1u);
-          if (ba >= 0) atomicAdd(my + 64 + ba, 1u);
-        }
-      }
+  iter15_global_phase<UPDATE, HIST>(fl, fh, Mout, R, flow_out, flow_hist, w, h, pair, ox0, oy0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA-staged variant of the winSize-15 iteration (the production path when rows are 16-byte
+// aligned, i.e. w % 4 == 0).  The 46 x 64 raw tile of each M plane (tile + 7-pixel halo, box
+// padded to 64 columns = 256 B) is fetched by ONE cp.async.bulk.tensor issued by one thread into
+// a two-stage shared-memory ring (plane c+2 is in flight while plane c is consumed; completion
+// through an mbarrier).  This removes the 110 per-thread global loads of the LDG variant above
+// and all their 64-bit address arithmetic from the vertical pass (shared loads with immediate
+// offsets instead) and keeps HBM latency off the critical path.  Out-of-image elements are
+// zero-filled by TMA; tiles touching the image border therefore take a clamped-index read path
+// (replicate border, as OpenCV's box filter).
+// ---------------------------------------------------------------------------------------------
+constexpr int kTmRawW = 64;                               // box width (>= kFiRawW = 62, 256-byte rows)
+constexpr int kTmRawH = kFiTH + 2 * kFiM;                 // 46
+constexpr int kTmStageFloats = kTmRawW * kTmRawH;         // 2944 floats = 11776 B per stage
+constexpr unsigned kTmStageBytes = kTmStageFloats * sizeof(float);
+
+#ifdef STB_CPU_EMU
+struct TmaMap3D {            // emulator stand-in for a CUtensorMap over [planes][h][w] floats
+  const float* base;
+  int w, h, planes;
+};
+#define STB_GRID_CONSTANT
+__device__ __forceinline__ void tma_mbar_init(unsigned long long*, int) {}
+// the emulated copy is synchronous in thread 0: a block barrier stands in for the mbarrier wait
+__device__ __forceinline__ void tma_mbar_wait(unsigned long long*, unsigned) { __syncthreads(); }
+__device__ __forceinline__ void tma_load_tile(float* dst, const TmaMap3D* m, int x0, int y0, int z, unsigned long long*) {
+  for (int r = 0; r < kTmRawH; ++r)
+    for (int c = 0; c < kTmRawW; ++c) {
+      const int x = x0 + c, y = y0 + r;
+      dst[r * kTmRawW + c] = (x >= 0 && x < m->w && y >= 0 && y < m->h) ? m->base[((size_t)z * m->h + y) * m->w + x] : 0.f;
     }
+}
+#else
+}  // namespace stb
+#include <cuda.h>
+namespace stb {
+typedef CUtensorMap TmaMap3D;
+#define STB_GRID_CONSTANT __grid_constant__
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tma_mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned addr = smem_u32(bar);
+  // try_wait suspends for a hardware-defined time slice; bound the retries so that a faulty
+  // descriptor traps (reported as a launch failure) instead of hanging the GPU
+  for (unsigned spin = 0; spin < (1u << 24); ++spin) {
+    unsigned done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
   }
+  __trap();
+}
+__device__ __forceinline__ void tma_load_tile(float* dst, const TmaMap3D* map, int x0, int y0, int z, unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(kTmStageBytes) : "memory");
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<unsigned long long>(map)), "r"(x0), "r"(y0), "r"(z), "r"(smem_u32(bar))
+      : "memory");
+}
+#endif
+
+template <bool UPDATE, bool HIST>
+__global__ void __launch_bounds__(kFiThreads, 4)
+iter15_tma_kernel(const STB_GRID_CONSTANT TmaMap3D map_in, float* __restrict__ Mout, const float* __restrict__ R,
+                  PtrBatch<float> flow_out, int32_t* __restrict__ flow_hist, int w, int h, int pair0) {
+  __shared__ __align__(128) float raw[2][kTmStageFloats];     // also reused for the staged flow after the box phase
+  __shared__ float Vt[2][kFiVtWords];
+  __shared__ __align__(8) unsigned long long bars[2];
+  __shared__ unsigned fh[HIST ? (kFiThreads / 32) * STB_FLOWHIST_INTS : 1];
+  float2* fl = reinterpret_cast<float2*>(&raw[0][0]);       // 32 x 49 float2 = 12544 B <= one stage + part of the next
+  static_assert(kFiTH * kFiFlStride * sizeof(float2) <= 2 * kTmStageBytes, "staged flow must fit in the raw ring");
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pair = pair0 + blockIdx.z;
+  const int ox0 = blockIdx.x * kFiTW, oy0 = blockIdx.y * kFiTH;
+  const int bx0 = ox0 - kFiM, by0 = oy0 - kFiM;             // box origin (may be negative)
+
   if (HIST) {
-    __syncthreads();
-    if (tid < STB_FLOWHIST_INTS) {
-      unsigned sum = 0;
+    for (int i = tid; i < (kFiThreads / 32) * STB_FLOWHIST_INTS; i += kFiThreads) fh[i] = 0u;
+  }
+  if (tid == 0) {
+    tma_mbar_init(&bars[0], 1);
+    tma_mbar_init(&bars[1], 1);
+#ifndef STB_CPU_EMU
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+  }
+  __syncthreads();
+  if (tid == 0) {
+    tma_load_tile(raw[0], &map_in, bx0, by0, pair * 5 + 0, &bars[0]);
+    tma_load_tile(raw[1], &map_in, bx0, by0, pair * 5 + 1, &bars[1]);
+  }
+
+  // vertical item of this thread
+  const bool vact = tid < kFiRawW * 4;
+  const int vg = tid / kFiRawW, vcx = tid - vg * kFiRawW;
+  // tiles whose box pokes outside the image read through clamped indices (replicate border)
+  const bool border = (bx0 < 0) || (by0 < 0) || (bx0 + kFiRawW > w) || (by0 + kTmRawH > h);
+  const int ccol = min(max(bx0 + vcx, 0), w - 1) - bx0;      // clamped column inside the box
+
+  float sums[5][kFiGC];
 #pragma unroll
-      for (int wq = 0; wq < kFiThreads / 32; ++wq) sum += fh[wq * STB_FLOWHIST_INTS + tid];
-      if (sum) atomicAdd(flow_hist + (size_t)pair * STB_FLOWHIST_INTS + tid, (int)sum);
+  for (int c = 0; c < 5; ++c) {
+    const int st = c & 1;
+    tma_mbar_wait(&bars[st], (unsigned)((c >> 1) & 1));
+    float* vt = Vt[st];
+    if (vact) {
+      float v[kFiRows];
+      if (!border) {
+        const float* col = &raw[st][(vg * 8) * kTmRawW + vcx];
+#pragma unroll
+        for (int j = 0; j < kFiRows; ++j) v[j] = col[j * kTmRawW];
+      } else {
+#pragma unroll
+        for (int j = 0; j < kFiRows; ++j) {
+          const int rr = min(max(by0 + vg * 8 + j, 0), h - 1) - by0;
+          v[j] = raw[st][rr * kTmRawW + ccol];
+        }
+      }
+      float vs[8];
+      box15<8>(v, vs);
+      float* o = vt + vcx * 33 + vg * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = vs[i];
+    }
+    __syncthreads();                                           // raw[st] consumed, Vt[st] complete
+    if (tid == 0 && c + 2 < 5) tma_load_tile(raw[st], &map_in, bx0, by0, pair * 5 + c + 2, &bars[st]);
+    {
+      const float* rowp = vt + (warp * kFiGC) * 33 + lane;
+      float t[kFiGC + 14];
+#pragma unroll
+      for (int j = 0; j < kFiGC + 14; ++j) t[j] = rowp[j * 33];
+      box15<kFiGC>(t, sums[c]);
     }
   }
+  __syncthreads();   // every read of raw (plane 4 lives in stage 0) is done before fl aliases it
+
+  const float inv_area = 1.f / 225.f;
+#pragma unroll
+  for (int i = 0; i < kFiGC; ++i) {
+    const float g11 = sums[0][i] * inv_area, g12 = sums[1][i] * inv_area, g22 = sums[2][i] * inv_area;
+    const float h1 = sums[3][i] * inv_area, h2 = sums[4][i] * inv_area;
+    const float w12 = g12 * g12;
+    const float det = fmaf(g11, g22, -w12) + fmaf(-g12, g12, w12);
+    const float idet = 1.f / (det + 1e-3f);
+    const float t1 = g12 * h1;
+    const float nx = fmaf(g11, h2, -t1) + fmaf(-g12, h1, t1);
+    const float t2 = g12 * h2;
+    const float ny = fmaf(g22, h1, -t2) + fmaf(-g12, h2, t2);
+    fl[lane * kFiFlStride + warp * kFiGC + i] = make_float2(nx * idet, ny * idet);
+  }
+  __syncthreads();
+
+  iter15_global_phase<UPDATE, HIST>(fl, fh, Mout, R, flow_out, flow_hist, w, h, pair, ox0, oy0);
 }
 
 }  // namespace stb
@@ -904,6 +1078,9 @@ struct stb_farneback {
   // debug taps
   int dbg_level, dbg_pair;
   float *dbg_I0, *dbg_I1, *dbg_R0, *dbg_R1, *dbg_M0, *dbg_flow;
+  // TMA descriptors of the two M ping-pong buffers at every level ([5*P planes][h_k][w_k] floats)
+  TmaMap3D tmap[2][kMaxScales];
+  int use_tma[kMaxScales];
   // measurement hook: event pairs around the level-0 update-iteration kernels
   int profile;
   std::vector<cudaEvent_t> ev_free;
@@ -1014,6 +1191,43 @@ static int plan_levels(int W, int H, const stb_farneback_params& p, int* ws, int
   return levels + 1;
 }
 
+#ifdef STB_CPU_EMU
+static bool make_tmap(TmaMap3D* m, float* base, int w, int h, int planes) {
+  m->base = base; m->w = w; m->h = h; m->planes = planes;
+  return true;
+}
+#else
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(sym);
+    else
+      (void)cudaGetLastError();
+  }
+  return fn;
+}
+// [planes][h][w] f32, box = 64 x 46 x 1, zero fill outside the tensor
+static bool make_tmap(TmaMap3D* m, float* base, int w, int h, int planes) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc || (w & 3) != 0 || (reinterpret_cast<uintptr_t>(base) & 15u) != 0) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)planes};
+  const cuuint64_t strides[2] = {(cuuint64_t)w * sizeof(float), (cuuint64_t)w * h * sizeof(float)};
+  const cuuint32_t box[3] = {(cuuint32_t)kTmRawW, (cuuint32_t)kTmRawH, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+#endif
+
 struct WsLayout { size_t gray, I, R, M, flow, total; };
 
 static WsLayout ws_layout(int W, int H, int P, int nscales, const int* ws, const int* hs) {
@@ -1123,6 +1337,18 @@ int stb_farneback_create(int width, int height, int max_pairs, const stb_farneba
   h->M[1] = (float*)(base + off); off += l.M;
   h->flow[0] = (float*)(base + off); off += l.flow;
   h->flow[1] = (float*)(base + off); off += l.flow;
+  {
+    const char* no_tma = getenv("STB_NO_TMA");   // A/B knob: fall back to the LDG variant
+    for (int k = 0; k < h->nscales; ++k) {
+      h->use_tma[k] = 0;
+      if (no_tma && no_tma[0] == '1') continue;
+      // one box (64 x 46) must make sense for the level; tiny levels keep the LDG kernel
+      if (h->w[k] < kTmRawW || h->h[k] < 8) continue;
+      if (make_tmap(&h->tmap[0][k], h->M[0], h->w[k], h->h[k], 5 * max_pairs) &&
+          make_tmap(&h->tmap[1][k], h->M[1], h->w[k], h->h[k], 5 * max_pairs))
+        h->use_tma[k] = 1;
+    }
+  }
 #ifndef STB_CPU_EMU
   e = cudaFuncSetAttribute(iter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iter_smem_bytes(kItMaxHalo));
   if (e == cudaSuccess)
@@ -1274,7 +1500,10 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
       for (int it = 0; it < h->prm.num_iters; ++it) {
         if (it < h->prm.num_iters - 1) {
           if (prof && it == 0) { int prc = prof_mark(h, s); if (prc) return prc; }
-          if (fast15)
+          if (fast15 && h->use_tma[k])
+            stb_launch(iter15_tma_kernel<true, false>, grid, dim3(kFiThreads), 0, s, h->tmap[mc][k], h->M[mc ^ 1],
+                       (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0);
+          else if (fast15)
             stb_launch(iter15_kernel<true, false>, grid, dim3(kFiThreads), 0, s, (const float*)h->M[mc], h->M[mc ^ 1],
                        (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0);
           else
@@ -1288,7 +1517,13 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
             h->prof_pair_iters += (long long)(h->prm.num_iters - 1) * np;
           }
         } else {
-          if (fast15 && k == 0 && d_hist != nullptr)
+          if (fast15 && h->use_tma[k] && k == 0 && d_hist != nullptr)
+            stb_launch(iter15_tma_kernel<false, true>, grid, dim3(kFiThreads), 0, s, h->tmap[mc][k], (float*)nullptr,
+                       (const float*)h->R, fo, d_hist, w, hh, p0);
+          else if (fast15 && h->use_tma[k])
+            stb_launch(iter15_tma_kernel<false, false>, grid, dim3(kFiThreads), 0, s, h->tmap[mc][k], (float*)nullptr,
+                       (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0);
+          else if (fast15 && k == 0 && d_hist != nullptr)
             stb_launch(iter15_kernel<false, true>, grid, dim3(kFiThreads), 0, s, (const float*)h->M[mc], (float*)nullptr,
                        (const float*)h->R, fo, d_hist, w, hh, p0);
           else if (fast15)

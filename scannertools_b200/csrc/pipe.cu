@@ -164,15 +164,18 @@ int stb_pipe_flow(stb_pipe* p, const uint8_t* h_frames, int n, float* h_flow, in
   const int B = p->B;
   std::vector<const uint8_t*> fr((size_t)B + 1);
   std::vector<float*> fl((size_t)B);
-  int c = 0;
-  for (int p0 = 0; p0 < n; p0 += B, ++c) {
-    const int m = n - p0 < B ? n - p0 : B;
+  int c = 0, prev_m = 0;
+  for (int p0 = 0; p0 < n; ++c) {
+    // The first upload of a call cannot overlap any compute: keep it short (a quarter batch),
+    // then full batches whose upload hides behind the previous batch's kernels.
+    const int cap = (c == 0 && n > B) ? (B >= 4 ? B / 4 : 1) : B;
+    const int m = n - p0 < cap ? n - p0 : cap;
     const int slot = c & 1;
     STB_CUDA(cudaStreamWaitEvent(p->s_copy, p->comp_done[slot], 0));
     int first = 0;
     if (c > 0) {
       // frame p0 is the last frame of the previous batch: device-to-device, not over PCIe again
-      STB_CUDA(cudaMemcpyAsync(p->d_frames[slot], p->d_frames[slot ^ 1] + (size_t)B * stride, fbytes, cudaMemcpyDeviceToDevice, p->s_copy));
+      STB_CUDA(cudaMemcpyAsync(p->d_frames[slot], p->d_frames[slot ^ 1] + (size_t)prev_m * stride, fbytes, cudaMemcpyDeviceToDevice, p->s_copy));
       first = 1;
     }
     if (stride == fbytes) {
@@ -202,8 +205,8 @@ int stb_pipe_flow(stb_pipe* p, const uint8_t* h_frames, int n, float* h_flow, in
                                cudaMemcpyDeviceToHost, p->s_out));
       STB_CUDA(cudaEventRecord(p->out_done[slot], p->s_out));
     }
-    // a partial last batch must still leave its last frame where the next batch expects it;
-    // only full batches are followed by another batch, so slot[B] is always the halo frame.
+    prev_m = m;   // the next batch's frame 0 is this batch's frame m
+    p0 += m;
   }
   if (h_flow_hist)
     STB_CUDA(cudaMemcpyAsync(h_flow_hist, p->d_res, (size_t)n * STB_FLOWHIST_INTS * sizeof(int32_t), cudaMemcpyDeviceToHost, p->s_comp));
