@@ -890,7 +890,8 @@ iter15_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const flo
 // aligned, i.e. w % 4 == 0).  The 46 x 64 raw tile of each M plane (tile + 7-pixel halo, box
 // padded to 64 columns = 256 B) is fetched by ONE cp.async.bulk.tensor issued by one thread into
 // a two-stage shared-memory ring (plane c+2 is in flight while plane c is consumed; completion
-// through an mbarrier).  This removes the 110 per-thread global loads of the LDG variant above
+// through an mbarrier).  The box starts at x = tile_x - 8 so that its innermost coordinate is a
+// multiple of 4 floats (TMA faults on an unaligned inner coordinate).  This removes the 110 per-thread global loads of the LDG variant above
 // and all their 64-bit address arithmetic from the vertical pass (shared loads with immediate
 // offsets instead) and keeps HBM latency off the critical path.  Out-of-image elements are
 // zero-filled by TMA; tiles touching the image border therefore take a clamped-index read path
@@ -911,6 +912,7 @@ __device__ __forceinline__ void tma_mbar_init(unsigned long long*, int) {}
 // the emulated copy is synchronous in thread 0: a block barrier stands in for the mbarrier wait
 __device__ __forceinline__ void tma_mbar_wait(unsigned long long*, unsigned) { __syncthreads(); }
 __device__ __forceinline__ void tma_load_tile(float* dst, const TmaMap3D* m, int x0, int y0, int z, unsigned long long*) {
+  if (x0 & 3) { fprintf(stderr, "cuda_emu: TMA inner coordinate %d is not 16-byte aligned\n", x0); abort(); }
   for (int r = 0; r < kTmRawH; ++r)
     for (int c = 0; c < kTmRawW; ++c) {
       const int x = x0 + c, y = y0 + r;
@@ -965,11 +967,14 @@ iter15_tma_kernel(const STB_GRID_CONSTANT TmaMap3D map_in, float* __restrict__ M
   __shared__ unsigned fh[HIST ? (kFiThreads / 32) * STB_FLOWHIST_INTS : 1];
   float2* fl = reinterpret_cast<float2*>(&raw[0][0]);       // 32 x 49 float2 = 12544 B <= one stage + part of the next
   static_assert(kFiTH * kFiFlStride * sizeof(float2) <= 2 * kTmStageBytes, "staged flow must fit in the raw ring");
+  static_assert(kFiRawW + 1 <= kTmRawW && (kFiTW % 4) == 0, "box covers the halo'd tile from an aligned origin");
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pair = pair0 + blockIdx.z;
   const int ox0 = blockIdx.x * kFiTW, oy0 = blockIdx.y * kFiTH;
-  const int bx0 = ox0 - kFiM, by0 = oy0 - kFiM;             // box origin (may be negative)
+  // box origin (may be negative).  The innermost TMA coordinate must be 16-byte aligned (measured:
+  // an unaligned x traps), so the box starts one column early: raw column cx lives at box column cx+1.
+  const int bx0 = ox0 - kFiM - 1, by0 = oy0 - kFiM;
 
   if (HIST) {
     for (int i = tid; i < (kFiThreads / 32) * STB_FLOWHIST_INTS; i += kFiThreads) fh[i] = 0u;
@@ -991,8 +996,8 @@ iter15_tma_kernel(const STB_GRID_CONSTANT TmaMap3D map_in, float* __restrict__ M
   const bool vact = tid < kFiRawW * 4;
   const int vg = tid / kFiRawW, vcx = tid - vg * kFiRawW;
   // tiles whose box pokes outside the image read through clamped indices (replicate border)
-  const bool border = (bx0 < 0) || (by0 < 0) || (bx0 + kFiRawW > w) || (by0 + kTmRawH > h);
-  const int ccol = min(max(bx0 + vcx, 0), w - 1) - bx0;      // clamped column inside the box
+  const bool border = (bx0 + 1 < 0) || (by0 < 0) || (bx0 + 1 + kFiRawW > w) || (by0 + kTmRawH > h);
+  const int ccol = min(max(bx0 + 1 + vcx, 0), w - 1) - bx0;  // clamped column inside the box
 
   float sums[5][kFiGC];
 #pragma unroll
@@ -1003,7 +1008,7 @@ iter15_tma_kernel(const STB_GRID_CONSTANT TmaMap3D map_in, float* __restrict__ M
     if (vact) {
       float v[kFiRows];
       if (!border) {
-        const float* col = &raw[st][(vg * 8) * kTmRawW + vcx];
+        const float* col = &raw[st][(vg * 8) * kTmRawW + vcx + 1];
 #pragma unroll
         for (int j = 0; j < kFiRows; ++j) v[j] = col[j * kTmRawW];
       } else {
