@@ -142,6 +142,17 @@ STB_API int stb_farneback_levels(const stb_farneback* h, int* widths /* 8 */, in
 STB_API int stb_farneback_debug_set(stb_farneback* h, int level, int pair, float* d_I0, float* d_I1,
                                     float* d_R0, float* d_R1, float* d_M0, float* d_flow_level);
 
+/* ---- Resize (the op in front of OpticalFlow in old/histograms.py:64-68) ---
+ * Replaces cv::resize / cvc::resize(img, out, Size(w, h), 0, 0, INTER_LINEAR) on 8-bit frames
+ * (scannertools_cpp/imgproc/resize_kernel.cpp:69-79); bit-exact with OpenCV's fixed-point
+ * bilinear (including its INTER_AREA fast path for exact 2x down-scaling).  channels: 1, 3, 4.
+ * stb_resize_target reproduces the op's target-size rules (width/height/min/preserve_aspect,
+ * resize_kernel.cpp:43-61). */
+STB_API int stb_resize_target(int frame_w, int frame_h, int width, int height, int min_flag, int preserve_aspect,
+                              int* out_w, int* out_h);
+STB_API int stb_resize_bilinear_u8(const uint8_t* const* d_src, int n, int src_w, int src_h, int channels,
+                                   uint8_t* const* d_dst, int dst_w, int dst_h, stb_stream_t stream);
+
 /* ---- measurement hooks (bench.py) -----------------------------------------------------------
  * stb_launch_count: kernels this library has launched in this process (all entry points).
  * stb_farneback_profile: when enabled, every level-0 pair brackets its fused update-iteration

@@ -87,3 +87,9 @@ def shot_boundaries(hists):
         if diffs[i] - np.mean(window) > 2.5 * np.std(window):
             boundaries.append(i)
     return boundaries
+
+
+def resize(frame, width, height):
+    """Resize op with the default interpolation (scannertools_cpp/imgproc/resize_kernel.cpp:31-35,69-71):
+    cv::resize(img, out, Size(width, height), 0, 0, INTER_LINEAR)."""
+    return cv2.resize(frame, (width, height), interpolation=cv2.INTER_LINEAR)

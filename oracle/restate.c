@@ -483,3 +483,56 @@ ORC_API void orc_optical_flow_rgb(const uint8_t* rgb0, const uint8_t* rgb1, int 
   orc_farneback(g0, g1, W, H, flow_out);
   free(g0); free(g1);
 }
+
+/* ---- Resize (next row): cv::resize INTER_LINEAR on 8-bit frames ---------
+ * scannertools_cpp/imgproc/resize_kernel.cpp:69-71.  OpenCV's 8U path is fixed point:
+ * 11-bit coefficients (cvRound(f * 2048)), horizontal pass to int, vertical pass
+ * (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.  x source index/fraction are
+ * clamped when the coefficients are built; y keeps the unclamped fraction and clips the two row
+ * indices.  Exact 2x down-scaling in both directions takes the INTER_AREA fast path
+ * (a + b + c + d + 2) >> 2.  Verified bit-exact against cv2 4.13 (tests/test_oracle.py). */
+ORC_API void orc_resize_linear_u8(const uint8_t* src, int sw, int sh, int cn, uint8_t* dst, int dw, int dh) {
+  if (sw == 2 * dw && sh == 2 * dh) {
+    for (int y = 0; y < dh; ++y)
+      for (int x = 0; x < dw; ++x)
+        for (int c = 0; c < cn; ++c) {
+          const uint8_t* p = src + ((size_t)(2 * y) * sw + 2 * x) * cn + c;
+          dst[((size_t)y * dw + x) * cn + c] = (uint8_t)((p[0] + p[cn] + p[(size_t)sw * cn] + p[(size_t)sw * cn + cn] + 2) >> 2);
+        }
+    return;
+  }
+  double scale_x = 1. / ((double)dw / sw), scale_y = 1. / ((double)dh / sh);
+  int* xofs = (int*)malloc(sizeof(int) * dw);
+  int* xa = (int*)malloc(sizeof(int) * dw * 2);
+  for (int dx = 0; dx < dw; ++dx) {
+    float fx = (float)((dx + 0.5) * scale_x - 0.5);
+    int sx = cv_floor_f(fx);
+    fx -= sx;
+    if (sx < 0) { fx = 0; sx = 0; }
+    if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+    xofs[dx] = sx;
+    xa[dx * 2] = cv_round((double)((1.f - fx) * 2048.f));
+    xa[dx * 2 + 1] = cv_round((double)(fx * 2048.f));
+  }
+  for (int dy = 0; dy < dh; ++dy) {
+    float fy = (float)((dy + 0.5) * scale_y - 0.5);
+    int sy = cv_floor_f(fy);
+    fy -= sy;
+    int b0 = cv_round((double)((1.f - fy) * 2048.f)), b1 = cv_round((double)(fy * 2048.f));
+    int y0 = sy < 0 ? 0 : (sy > sh - 1 ? sh - 1 : sy);
+    int y1 = sy + 1 < 0 ? 0 : (sy + 1 > sh - 1 ? sh - 1 : sy + 1);
+    const uint8_t* r0 = src + (size_t)y0 * sw * cn;
+    const uint8_t* r1 = src + (size_t)y1 * sw * cn;
+    for (int dx = 0; dx < dw; ++dx) {
+      int sx = xofs[dx], sx1 = sx + 1 < sw ? sx + 1 : sx;
+      int a0 = xa[dx * 2], a1 = xa[dx * 2 + 1];
+      for (int c = 0; c < cn; ++c) {
+        int h0 = r0[sx * cn + c] * a0 + r0[sx1 * cn + c] * a1;
+        int h1 = r1[sx * cn + c] * a0 + r1[sx1 * cn + c] * a1;
+        int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        dst[((size_t)dy * dw + dx) * cn + c] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+      }
+    }
+  }
+  free(xofs); free(xa);
+}

@@ -121,3 +121,12 @@ def optical_flow(frame0, frame1):
     out = np.empty((H, W, 2), np.float32)
     lib().orc_optical_flow_rgb(_p(f0), _p(f1), C.c_int(W), C.c_int(H), _p(out))
     return out
+
+
+def resize(frame, width, height):
+    f = np.ascontiguousarray(frame, np.uint8)
+    sh, sw = f.shape[:2]
+    cn = f.shape[2] if f.ndim == 3 else 1
+    out = np.empty((height, width) + ((cn,) if f.ndim == 3 else ()), np.uint8)
+    lib().orc_resize_linear_u8(_p(f), C.c_int(sw), C.c_int(sh), C.c_int(cn), _p(out), C.c_int(width), C.c_int(height))
+    return out

@@ -160,6 +160,43 @@ def frame_difference(prev, cur, stream=None):
     return out
 
 
+def resize_target(frame_w, frame_h, width=0, height=0, min=False, preserve_aspect=False):
+    """Target size of the Resize op for ResizeArgs(width, height, min, preserve_aspect)
+    (scannertools_cpp/imgproc/resize_kernel.cpp:43-61)."""
+    lib = _lib.load()
+    w, h = C.c_int(), C.c_int()
+    _lib.check(lib.stb_resize_target(frame_w, frame_h, int(width), int(height), 1 if min else 0,
+                                     1 if preserve_aspect else 0, C.byref(w), C.byref(h)), lib)
+    return w.value, h.value
+
+
+def resize(frames, width=0, height=0, min=False, preserve_aspect=False, interpolation='INTER_LINEAR', stream=None):
+    """Resize op (scannertools_cpp/imgproc/resize_kernel.cpp:22-105) on uint8 frames: n frames ->
+    [n, height, width, C], bit-exact with cv::resize INTER_LINEAR.  Only the default interpolation
+    is implemented (the reference silently falls back to INTER_LINEAR for unknown names, :31-35)."""
+    torch = _torch()
+    lib = _lib.load()
+    if interpolation != 'INTER_LINEAR':
+        raise NotImplementedError('Resize: only INTER_LINEAR is implemented (got %r)' % (interpolation,))
+    if isinstance(frames, torch.Tensor) and frames.dim() == 3:
+        frames = frames.unsqueeze(0)
+    lst = [frames[i] for i in range(frames.shape[0])] if isinstance(frames, torch.Tensor) else list(frames)
+    for f in lst:
+        _require_cuda(f, torch.uint8, 'frames')
+    if not lst:
+        raise ValueError('Resize needs at least one frame')
+    H, W, c = lst[0].shape
+    tw, th = resize_target(W, H, width, height, min, preserve_aspect)
+    if tw <= 0 or th <= 0:
+        raise ValueError('Resize: target size %dx%d' % (tw, th))
+    out = torch.empty((len(lst), th, tw, c), dtype=torch.uint8, device=lst[0].device)
+    with torch.cuda.device(lst[0].device):
+        st = _lib.ptr_table([f.data_ptr() for f in lst])
+        dt = _lib.ptr_table([out[i].data_ptr() for i in range(len(lst))])
+        _lib.check(lib.stb_resize_bilinear_u8(st, len(lst), W, H, c, dt, tw, th, _stream_ptr(stream)), lib)
+    return out
+
+
 class OpticalFlow:
     """OpticalFlow op (dense Farneback, the reference's hard-coded parameters).
 

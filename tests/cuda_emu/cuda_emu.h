@@ -128,6 +128,7 @@ static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; retu
 static inline float __fsqrt_rn(float a) { return std::sqrt(a); }
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 static inline int __float2int_rd(float a) { return (int)std::floor(a); }
+static inline int __float2int_rn(float a) { return (int)std::nearbyint(a); }
 static inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline int __double2int_rd(double a) { return (int)std::floor(a); }

@@ -69,6 +69,15 @@ def main():
     a = synth.noise_clip(21, 2, 19, 23)
     np.savez_compressed(os.path.join(HERE, 'framediff.npz'), prev=a[0], cur=a[1],
                         out=cv2_ops.frame_difference(a[0], a[1]), meta=str(meta))
+    # Resize (next row): down-scale to the shipped pipeline's 426x240, exact 2x, up-scale, gray
+    rs = {}
+    rng = np.random.default_rng(31)
+    for name, (sw, sh, dw, dh, cn) in [('270p_to_213x120', (480, 270, 213, 120, 3)), ('half', (128, 96, 64, 48, 3)),
+                                       ('up', (64, 48, 200, 100, 3)), ('gray_odd', (101, 77, 33, 20, 1))]:
+        img = rng.integers(0, 256, (sh, sw, cn) if cn > 1 else (sh, sw), dtype=np.uint8)
+        rs['in_' + name] = img
+        rs['out_' + name] = cv2_ops.resize(img, dw, dh)
+    np.savez_compressed(os.path.join(HERE, 'resize.npz'), meta=str(meta), **rs)
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -148,6 +148,21 @@ def test_emu_farneback_generic_window(emu):
     assert emu.stb_farneback_create(w, h, 1, C.byref(bad), C.byref(hd)) != 0
 
 
+def test_emu_resize_bit_exact(emu):
+    rng = np.random.default_rng(1)
+    for (sw, sh, dw, dh, cn) in [(213, 120, 107, 60, 3), (64, 48, 32, 24, 3), (64, 48, 200, 100, 3), (101, 77, 33, 20, 1), (40, 30, 40, 30, 4)]:
+        img = rng.integers(0, 256, (sh, sw, cn), dtype=np.uint8)
+        out = np.zeros((dh, dw, cn), np.uint8)
+        assert emu.stb_resize_bilinear_u8(_lib.ptr_table([img.ctypes.data]), 1, sw, sh, cn, _lib.ptr_table([out.ctypes.data]), dw, dh, None) == 0
+        assert np.array_equal(out, restate.resize(img, dw, dh)), (sw, sh, dw, dh, cn)
+    w, h = C.c_int(), C.c_int()
+    # ResizeArgs semantics of resize_kernel.cpp:43-61
+    assert emu.stb_resize_target(1920, 1080, 426, 0, 0, 1, C.byref(w), C.byref(h)) == 0 and (w.value, h.value) == (426, 239)
+    assert emu.stb_resize_target(1920, 1080, 0, 240, 0, 1, C.byref(w), C.byref(h)) == 0 and (w.value, h.value) == (426, 240)
+    assert emu.stb_resize_target(320, 240, 426, 240, 1, 0, C.byref(w), C.byref(h)) == 0 and (w.value, h.value) == (320, 240)
+    assert emu.stb_resize_bilinear_u8(_lib.ptr_table([0]), 1, 4, 4, 2, _lib.ptr_table([0]), 2, 2, None) != 0   # 2 channels: unsupported
+
+
 def test_emu_pipe_host_path(emu):
     h, w = 48, 64
     clip = synth.textured_clip(5, 6, h, w)

@@ -170,6 +170,25 @@ def test_frame_difference(torch, ops, golden):
     assert np.array_equal(out, (a[1].astype(np.int16) - a[0].astype(np.int16)).astype(np.uint8))
 
 
+# ------------------------------------------------------------------ Resize (next row, 8f rank 1)
+def test_resize_goldens_and_pipeline_size(torch, ops, golden):
+    g = golden('resize.npz')
+    for nme in [k[3:] for k in g.files if k.startswith('in_')]:
+        src, ref = g['in_' + nme], g['out_' + nme]
+        if src.ndim == 2:
+            src, ref = src[..., None], ref[..., None]
+        out = ops.resize(dev(torch, src), width=ref.shape[1], height=ref.shape[0]).cpu().numpy()[0]
+        assert np.array_equal(out, ref), nme
+    # the shipped flow-histogram pipeline: Resize(426x240) -> OpticalFlow (old/histograms.py:64-68)
+    fr = synth.noise_clip(9, 3, 1080, 1920)
+    out = ops.resize(dev(torch, fr), width=426, height=240).cpu().numpy()
+    for i in range(3):
+        assert np.array_equal(out[i], (cvo or restate).resize(fr[i], 426, 240)), i
+    assert ops.resize_target(1920, 1080, width=426, preserve_aspect=True) == (426, 239)
+    with pytest.raises(NotImplementedError):
+        ops.resize(dev(torch, fr[:1]), width=10, height=10, interpolation='INTER_CUBIC')
+
+
 # ------------------------------------------------------------------ OpticalFlow
 FLOW_MEAN_TOL, FLOW_MAX_TOL = 1e-3, 1e-2   # px, north_star
 

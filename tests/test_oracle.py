@@ -66,6 +66,15 @@ def test_restate_frame_difference(golden):
     assert np.array_equal(restate.frame_difference(g['prev'], g['cur']), g['out'])
 
 
+def test_restate_resize(golden):
+    g = golden('resize.npz')
+    names = [k[3:] for k in g.files if k.startswith('in_')]
+    assert len(names) == 4
+    for nme in names:
+        out = g['out_' + nme]
+        assert np.array_equal(restate.resize(g['in_' + nme], out.shape[1], out.shape[0]), out), nme
+
+
 def test_cv2_matches_goldens(golden, have_cv2):
     if not have_cv2:
         pytest.skip('cv2 not importable')
@@ -78,5 +87,7 @@ def test_cv2_matches_goldens(golden, have_cv2):
     assert np.array_equal(cv2_ops.histogram(gh['in_noise_37x53']), gh['out_noise_37x53'])
     gf = golden('flowhist.npz')
     assert np.array_equal(cv2_ops.flow_histogram(gf['in_stress_213x120']), gf['out_stress_213x120'])
+    gr = golden('resize.npz')
+    assert np.array_equal(cv2_ops.resize(gr['in_up'], 200, 100), gr['out_up'])
     gs = golden('shot_c1.npz')
     assert cv2_ops.shot_boundaries(list(gs['hists'].reshape(-1, 3, 16))) == list(gs['boundaries'])

@@ -26,7 +26,8 @@ def test_ops_and_kernels_registered_under_reference_names(shim):
     """REGISTER_OP / REGISTER_KERNEL lines keep the reference's names, batching and stencils
     (histogram_kernel_gpu.cpp:79-82, optical_flow_kernel_cpu.cpp:51-54, optical_flow_kernel_gpu.cpp:109-112,
     flow_histogram_kernel_cpu.cpp:62-67, frame_difference_kernel_cpu.cpp:74-80)."""
-    expect = {b'Histogram': (1, 0, 0), b'OpticalFlow': (1, 0, 1), b'FlowHistogram': (1, 0, 0), b'FrameDifference': (0, -1, 0)}
+    expect = {b'Histogram': (1, 0, 0), b'OpticalFlow': (1, 0, 1), b'FlowHistogram': (1, 0, 0), b'FrameDifference': (0, -1, 0),
+              b'Resize': (1, 0, 0)}
     for op, (batched, lo, hi) in expect.items():
         b, l, h = C.c_int(-1), C.c_int(99), C.c_int(99)
         assert shim.stb_shim_registered(op, C.byref(b), C.byref(l), C.byref(h)) == 1, op
@@ -64,3 +65,37 @@ def test_frame_difference_kernel_class(shim):
     out = np.zeros_like(a[0])
     assert shim.stb_shim_frame_difference(P(a[0]), P(a[1]), 53, 37, 3, P(out), 0) == 0
     assert np.array_equal(out, restate.frame_difference(a[0], a[1]))
+
+
+def _resize_args(width=0, height=0, minflag=False, preserve_aspect=False, interpolation=b''):
+    """protobuf wire encoding of ResizeArgs (scannertools_imgproc.proto:33-39)."""
+    def varint(v):
+        out = bytearray()
+        while True:
+            b = v & 0x7f
+            v >>= 7
+            out.append(b | (0x80 if v else 0))
+            if not v:
+                return bytes(out)
+    buf = b''
+    if width: buf += b'\x08' + varint(width)
+    if height: buf += b'\x10' + varint(height)
+    if minflag: buf += b'\x18\x01'
+    if preserve_aspect: buf += b'\x20\x01'
+    if interpolation: buf += b'\x2a' + varint(len(interpolation)) + interpolation
+    return buf
+
+
+@pytest.mark.gpu
+def test_resize_kernel_class_with_serialized_args(shim):
+    fr = synth.noise_clip(6, 3, 270, 480)
+    args = _resize_args(width=213, preserve_aspect=True, interpolation=b'INTER_LINEAR')
+    out = np.zeros((3, 200, 300, 3), np.uint8).reshape(-1)
+    ow, oh = C.c_int(), C.c_int()
+    rc = shim.stb_shim_resize(P(fr), 3, 480, 270, 3, args, len(args), P(out), out.size, C.byref(ow), C.byref(oh), 0)
+    assert rc == 0 and (ow.value, oh.value) == (213, 270 * 213 // 480)
+    got = out[:3 * oh.value * ow.value * 3].reshape(3, oh.value, ow.value, 3)
+    for i in range(3):
+        assert np.array_equal(got[i], restate.resize(fr[i], ow.value, oh.value))
+    bad = _resize_args(width=10, height=10, interpolation=b'INTER_CUBIC')
+    assert shim.stb_shim_resize(P(fr), 1, 480, 270, 3, bad, len(bad), P(out), out.size, C.byref(ow), C.byref(oh), 0) == -4

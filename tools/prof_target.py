@@ -13,9 +13,11 @@ from scannertools_b200 import ops, synth  # noqa: E402
 
 def main():
     what = sys.argv[1:] or ['flow', 'hist', 'flowhist']
-    clip = synth.textured_clip(1, 3, 1080, 1920)
+    npairs = int(os.environ.get('PROF_PAIRS', '2'))
+    base = synth.textured_clip(1, 5, 1080, 1920)
+    clip = np.concatenate([base] * ((npairs + 5) // 5 + 1))[:npairs + 1]
     fr = torch.from_numpy(clip).cuda()
-    of = ops.OpticalFlow(1920, 1080, max_batch=2)
+    of = ops.OpticalFlow(1920, 1080, max_batch=npairs)
     f4k = torch.randint(0, 256, (8, 2160, 3840, 3), dtype=torch.uint8, device='cuda')
     flow = torch.randn((4, 1080, 1920, 2), device='cuda') * 5
 
