@@ -49,8 +49,10 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region: the sampler is started
+    before the warm-up (nvidia-smi takes a few hundred ms to start) and only rows whose timestamp
+    falls inside [t0, t1] of the timed region are kept."""
+    Q = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu_index):
@@ -70,12 +72,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -83,9 +85,17 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        import datetime
+        for seen, r in self.rows:
             f = [x.strip() for x in r.split(',')]
             if len(f) < 9:
+                continue
+            ts = seen
+            try:
+                ts = datetime.datetime.strptime(f[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+            except ValueError:
+                pass
+            if t0 is not None and not (t0 - 0.02 <= ts <= t1 + 0.02):
                 continue
             try:
                 sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
@@ -224,24 +234,26 @@ def run_ours(args):
             ot = _lib.ptr_table(flow_ptrs[b0:b0 + B])
             _lib.check(lib.stb_farneback_run_hist(of._h, ft, B, ot, C.c_void_p(d_fh[b0].data_ptr()), sp), lib)
 
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
     lib.stb_farneback_profile(of._h, 1)
     l0 = lib.stb_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    wall0 = time.time()
     ev0.record()
     for _ in range(args.steps):
         step_device()
     ev1.record()
     barrier()
+    wall1 = time.time()
     t_dev = ev0.elapsed_time(ev1) * 1e-3
     launches = lib.stb_launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     ms_total, nl, npi = C.c_double(), C.c_longlong(), C.c_longlong()
     _lib.check(lib.stb_farneback_profile_read(of._h, C.byref(ms_total), C.byref(nl), C.byref(npi)), lib)
     lib.stb_farneback_profile(of._h, 0)
@@ -297,7 +309,7 @@ def run_ours(args):
                          'launches_timed': int(nl_all),
                          'share_of_step': (ms_iter_all * 1e-3 / world) / t_dev if t_dev else None,
                          'traffic': NCU_TRAFFIC_BYTES_PER_PAIR * pairs_per_launch,
-                         'traffic_source': 'profiles/r01_ncu_full_table.txt (2-pair capture, scaled per pair)'},
+                         'traffic_source': 'profiles/r01_ncu_full_table.txt (16-pair launch of the same kernel)'},
             'e2e': {'value': total_frames / t_e2e, 'unit': 'frames/s',
                     'h2d_bytes_per_step': world * (P + 1) * H * W * 3 - world * (P // B - 1) * H * W * 3 * 0,
                     'd2h_bytes_per_step': world * P * 512, 'ms_per_step': 1e3 * t_e2e / args.steps,
@@ -314,10 +326,10 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of iter15_kernel<true,false> at level 0 from the
-# committed `ncu --set full` capture (profiles/r01_ncu_full_table.txt: grid (40,34,2), 248.1 MB read
-# + 64.5..65.1 MB written for 2 pairs), per PAIR; scaled by the pairs one bench launch processes.
-NCU_TRAFFIC_BYTES_PER_PAIR = 156.4e6
+# dram__bytes_read.sum + dram__bytes_write.sum of iter15_tma_kernel<true,false> at level 0 from the
+# committed `ncu --set full` capture (profiles/r01_ncu_full_table.txt: grid (40,34,16), 1.98 GB read
+# + 645 MB written for the 16 pairs of one launch), per PAIR; scaled by the pairs a bench launch processes.
+NCU_TRAFFIC_BYTES_PER_PAIR = (1.98e9 + 645e6) / 16
 
 
 def extra_workloads(torch, ops, lib, args):

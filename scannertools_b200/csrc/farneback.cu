@@ -443,25 +443,12 @@ polyexp_kernel(const float* __restrict__ I, float* __restrict__ R, int w, int h,
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float border_w(int d) { return d < 2 ? 0.14f : 0.4472f; }
 
-__device__ __forceinline__ void update_matrices_q(float q0, float q1, float q2, float q3, float q4,
-                                                  const float* __restrict__ R1, int n, int w, int h, int x, int y,
-                                                  float dx, float dy, float m[5]) {
-  // q0..q4 = R0's five planes at (x, y).  n = w*h <= 2^28 (checked at create), so 5*n fits an
-  // int: 32-bit offsets throughout
-  float fx = (float)x + dx, fy = (float)y + dy;
-  const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
-  fx -= (float)x1; fy -= (float)y1;
-  float r2, r3, r4, r5, r6;
-  if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
-    const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-    const float* p = R1 + (y1 * w + x1);
-#define STB_BILIN(pl) (a00 * __ldg(p + (pl) * n) + a01 * __ldg(p + (pl) * n + 1) + a10 * __ldg(p + (pl) * n + w) + a11 * __ldg(p + (pl) * n + w + 1))
-    r2 = STB_BILIN(0);
-    r3 = STB_BILIN(1);
-    r4 = STB_BILIN(2);
-    r5 = STB_BILIN(3);
-    r6 = STB_BILIN(4);
-#undef STB_BILIN
+// second half of UpdateMatrices: from R0's planes q0..q4 at (x, y) and the (interpolated) R1
+// values r2..r6 (`inside` false = the out-of-range branch) to the five M entries
+__device__ __forceinline__ void um_finish(float q0, float q1, float q2, float q3, float q4, bool inside,
+                                          float r2, float r3, float r4, float r5, float r6,
+                                          int w, int h, int x, int y, float dx, float dy, float m[5]) {
+  if (inside) {
     r4 = (q2 + r4) * 0.5f;
     r5 = (q3 + r5) * 0.5f;
     r6 = (q4 + r6) * 0.25f;
@@ -485,6 +472,59 @@ __device__ __forceinline__ void update_matrices_q(float q0, float q1, float q2, 
   m[2] = r5 * r5 + r6 * r6;
   m[3] = r4 * r2 + r6 * r3;
   m[4] = r6 * r2 + r5 * r3;
+}
+
+__device__ __forceinline__ void update_matrices_q(float q0, float q1, float q2, float q3, float q4,
+                                                  const float* __restrict__ R1, int n, int w, int h, int x, int y,
+                                                  float dx, float dy, float m[5]) {
+  // q0..q4 = R0's five planes at (x, y).  n = w*h <= 2^28 (checked at create), so 5*n fits an
+  // int: 32-bit offsets throughout
+  float fx = (float)x + dx, fy = (float)y + dy;
+  const int x1 = __float2int_rd(fx), y1 = __float2int_rd(fy);
+  fx -= (float)x1; fy -= (float)y1;
+  float r[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  const bool inside = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
+  if (inside) {
+    const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+    const float* p = R1 + (y1 * w + x1);
+#pragma unroll
+    for (int pl = 0; pl < 5; ++pl)
+      r[pl] = a00 * __ldg(p + pl * n) + a01 * __ldg(p + pl * n + 1) + a10 * __ldg(p + pl * n + w) + a11 * __ldg(p + pl * n + w + 1);
+  }
+  um_finish(q0, q1, q2, q3, q4, inside, r[0], r[1], r[2], r[3], r[4], w, h, x, y, dx, dy, m);
+}
+
+// Two horizontally adjacent pixels (x, y) and (x+1, y).  Their bilinear footprints in R1 almost
+// always overlap (the flow is a 15x15-window solution, so floor(x + dx) of neighbours differs by
+// exactly 1 except at integer crossings): then 3 columns x 2 rows per plane serve both pixels
+// instead of 4 + 4 loads.  Same values, same arithmetic: bit-identical to two single calls.
+__device__ __forceinline__ void update_matrices_pair(const float2 q[5], const float* __restrict__ R1, int n, int w, int h,
+                                                     int x, int y, float2 fa, float2 fb, float ma[5], float mb[5]) {
+  float fxa = (float)x + fa.x, fya = (float)y + fa.y;
+  float fxb = (float)(x + 1) + fb.x, fyb = (float)y + fb.y;
+  const int x1a = __float2int_rd(fxa), y1a = __float2int_rd(fya);
+  const int x1b = __float2int_rd(fxb), y1b = __float2int_rd(fyb);
+  const bool ina = (unsigned)x1a < (unsigned)(w - 1) && (unsigned)y1a < (unsigned)(h - 1);
+  const bool inb = (unsigned)x1b < (unsigned)(w - 1) && (unsigned)y1b < (unsigned)(h - 1);
+  if (ina && inb && x1b == x1a + 1 && y1b == y1a) {
+    fxa -= (float)x1a; fya -= (float)y1a; fxb -= (float)x1b; fyb -= (float)y1b;
+    const float a00 = (1.f - fxa) * (1.f - fya), a01 = fxa * (1.f - fya), a10 = (1.f - fxa) * fya, a11 = fxa * fya;
+    const float b00 = (1.f - fxb) * (1.f - fyb), b01 = fxb * (1.f - fyb), b10 = (1.f - fxb) * fyb, b11 = fxb * fyb;
+    const float* p = R1 + (y1a * w + x1a);
+    float ra[5], rb[5];
+#pragma unroll
+    for (int pl = 0; pl < 5; ++pl) {
+      const float t0 = __ldg(p + pl * n), t1 = __ldg(p + pl * n + 1), t2 = __ldg(p + pl * n + 2);
+      const float u0 = __ldg(p + pl * n + w), u1 = __ldg(p + pl * n + w + 1), u2 = __ldg(p + pl * n + w + 2);
+      ra[pl] = a00 * t0 + a01 * t1 + a10 * u0 + a11 * u1;
+      rb[pl] = b00 * t1 + b01 * t2 + b10 * u1 + b11 * u2;
+    }
+    um_finish(q[0].x, q[1].x, q[2].x, q[3].x, q[4].x, true, ra[0], ra[1], ra[2], ra[3], ra[4], w, h, x, y, fa.x, fa.y, ma);
+    um_finish(q[0].y, q[1].y, q[2].y, q[3].y, q[4].y, true, rb[0], rb[1], rb[2], rb[3], rb[4], w, h, x + 1, y, fb.x, fb.y, mb);
+  } else {
+    update_matrices_q(q[0].x, q[1].x, q[2].x, q[3].x, q[4].x, R1, n, w, h, x, y, fa.x, fa.y, ma);
+    update_matrices_q(q[0].y, q[1].y, q[2].y, q[3].y, q[4].y, R1, n, w, h, x + 1, y, fb.x, fb.y, mb);
+  }
 }
 
 __device__ __forceinline__ void update_matrices_px(const float* __restrict__ R0, const float* __restrict__ R1,
@@ -548,8 +588,7 @@ updmat_init_kernel(const float* __restrict__ R, const float* __restrict__ flow_c
     float2 q[5];
 #pragma unroll
     for (int c = 0; c < 5; ++c) q[c] = __ldg(reinterpret_cast<const float2*>(R0 + c * n + o));
-    update_matrices_q(q[0].x, q[1].x, q[2].x, q[3].x, q[4].x, R1, n, w, h, x, y, da.x, da.y, ma);
-    update_matrices_q(q[0].y, q[1].y, q[2].y, q[3].y, q[4].y, R1, n, w, h, x + 1, y, db.x, db.y, mb);
+    update_matrices_pair(q, R1, n, w, h, x, y, da, db, ma, mb);
 #pragma unroll
     for (int c = 0; c < 5; ++c) *reinterpret_cast<float2*>(Mo + c * n) = make_float2(ma[c], mb[c]);
   } else {
@@ -753,8 +792,7 @@ __device__ __forceinline__ void iter15_global_phase(const float2* fl, unsigned* 
         float2 q[5];
 #pragma unroll
         for (int c = 0; c < 5; ++c) q[c] = __ldg(reinterpret_cast<const float2*>(R0 + c * ni + o));
-        update_matrices_q(q[0].x, q[1].x, q[2].x, q[3].x, q[4].x, R1, ni, w, h, x, y, fa.x, fa.y, ma);
-        update_matrices_q(q[0].y, q[1].y, q[2].y, q[3].y, q[4].y, R1, ni, w, h, x + 1, y, fb.x, fb.y, mb);
+        update_matrices_pair(q, R1, ni, w, h, x, y, fa, fb, ma, mb);
       } else {
         update_matrices_px(R0, R1, ni, w, h, x, y, fa.x, fa.y, ma);
         if (two) update_matrices_px(R0, R1, ni, w, h, x + 1, y, fb.x, fb.y, mb);
