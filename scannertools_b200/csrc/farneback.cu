@@ -764,10 +764,8 @@ constexpr int kFiGC = 6;                      // output columns per horizontal i
 constexpr int kFiVtWords = kFiRawW * 33;      // one transposed vertical-sum buffer
 constexpr int kFiFlStride = kFiTW + 1;        // float2 row stride of the staged flow (bank spread)
 
-// Global-memory phase shared by both winSize-15 kernels.  Consecutive lanes own consecutive x
-// (unit stride): the R1 bilinear gathers of a warp then touch one or two 128-byte lines per
-// load.  (A two-adjacent-pixels-per-thread mapping with 8-byte R0 / M' accesses was measured
-// slower: its stride-2 gathers need ~3 L1 wavefronts per load and the kernel is L1-bound.)
+// Global-memory phase shared by both winSize-15 kernels: consecutive threads along x, two adjacent
+// pixels per thread (8-byte accesses of R0 / M' / flow when rows are 8-byte aligned, i.e. w even).
 template <bool UPDATE, bool HIST>
 __device__ __forceinline__ void iter15_global_phase(const float2* fl, unsigned* fh, float* __restrict__ Mout,
                                                     const float* __restrict__ R, const PtrBatch<float>& flow_out,
@@ -777,30 +775,58 @@ __device__ __forceinline__ void iter15_global_phase(const float2* fl, unsigned* 
   const float* R0 = R + (size_t)pair * 5 * n;
   const float* R1 = R0 + 5 * n;
   const int ni = (int)n;
-  float2* fo_base = UPDATE ? nullptr : reinterpret_cast<float2*>(flow_out.p[blockIdx.z]);
-#pragma unroll 2
-  for (int i = 0; i < (kFiTW * kFiTH) / kFiThreads; ++i) {
-    const int p = tid + i * kFiThreads;
-    const int ty = p / kFiTW, tx = p - ty * kFiTW;
+  const bool pair_ok = (w & 1) == 0;
+#pragma unroll 1
+  for (int i = 0; i < (kFiTW * kFiTH) / (2 * kFiThreads); ++i) {
+    const int p2 = tid + i * kFiThreads;            // pixel-pair index inside the tile
+    const int ty = p2 / (kFiTW / 2), tx = (p2 - ty * (kFiTW / 2)) * 2;
     const int x = ox0 + tx, y = oy0 + ty;
     if (x >= w || y >= h) continue;
-    const float2 f = fl[ty * kFiFlStride + tx];
+    const float2 fa = fl[ty * kFiFlStride + tx];
+    const float2 fb = fl[ty * kFiFlStride + tx + 1];
+    const bool two = (x + 1 < w);
     const int o = y * w + x;
     if (UPDATE) {
-      float mm[5];
-      update_matrices_px(R0, R1, ni, w, h, x, y, f.x, f.y, mm);
-      float* Mo = Mout + (size_t)pair * 5 * n + o;
+      float ma[5], mb[5];
+      if (two && pair_ok) {
+        float2 q[5];
 #pragma unroll
-      for (int c = 0; c < 5; ++c) Mo[c * ni] = mm[c];
+        for (int c = 0; c < 5; ++c) q[c] = __ldg(reinterpret_cast<const float2*>(R0 + c * ni + o));
+        update_matrices_pair(q, R1, ni, w, h, x, y, fa, fb, ma, mb);
+      } else {
+        update_matrices_px(R0, R1, ni, w, h, x, y, fa.x, fa.y, ma);
+        if (two) update_matrices_px(R0, R1, ni, w, h, x + 1, y, fb.x, fb.y, mb);
+      }
+      float* Mo = Mout + (size_t)pair * 5 * n + o;
+      if (two && pair_ok) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) *reinterpret_cast<float2*>(Mo + c * ni) = make_float2(ma[c], mb[c]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) { Mo[c * ni] = ma[c]; if (two) Mo[c * ni + 1] = mb[c]; }
+      }
     } else {
-      if (fo_base != nullptr) fo_base[o] = f;
+      if (flow_out.p[blockIdx.z] != nullptr) {
+        float2* fo = reinterpret_cast<float2*>(flow_out.p[blockIdx.z]) + o;
+        if (two && pair_ok && ((reinterpret_cast<uintptr_t>(fo) & 15u) == 0)) {
+          *reinterpret_cast<float4*>(fo) = make_float4(fa.x, fa.y, fb.x, fb.y);
+        } else {
+          fo[0] = fa;
+          if (two) fo[1] = fb;
+        }
+      }
       if (HIST) {
         // fused FlowHistogram (flow_histogram_kernel_cpu.cpp:33-49) of the flow just produced
         unsigned* my = fh + warp * STB_FLOWHIST_INTS;
         int bm, ba;
-        flow_bins_fast(f.x, f.y, bm, ba);
+        flow_bins_fast(fa.x, fa.y, bm, ba);
         if (bm >= 0) atomicAdd(my + bm, 1u);
         if (ba >= 0) atomicAdd(my + 64 + ba, 1u);
+        if (two) {
+          flow_bins_fast(fb.x, fb.y, bm, ba);
+          if (bm >= 0) atomicAdd(my + bm, 1u);
+          if (ba >= 0) atomicAdd(my + 64 + ba, 1u);
+        }
       }
     }
   }
