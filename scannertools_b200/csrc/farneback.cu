@@ -210,13 +210,25 @@ pyr_pow2_kernel(const uint8_t* __restrict__ gray, float* __restrict__ I, int W, 
   const int r_lo = S * oy0 + S / 2 - 1 - RAD;                  // first staged row
   if (tid < NT) taps[tid] = mt.c[tid];
 
-  const bool interior_x = (a_lo >= 0) && (a_lo + PITCH <= W) && ((W & 3) == 0);
-  if (interior_x) {
-    constexpr int WPR = PITCH / 4;
+  // Staging.  W is a multiple of S (>= 2) here; when it is also a multiple of 4 every aligned
+  // 4-byte word of a row lies entirely inside or entirely outside [0, W): inside words are one
+  // aligned load, the few outside words (tiles touching the left / right edge) are rebuilt byte
+  // by byte through REFLECT_101.
+  constexpr int WPR = PITCH / 4;
+  if ((W & 3) == 0) {
     for (int idx = tid; idx < NROWS * WPR; idx += 256) {
       const int rr = idx / WPR, wc = idx - rr * WPR;
       const int y = reflect101(r_lo + rr, H);
-      reinterpret_cast<unsigned*>(g8)[idx] = __ldg(reinterpret_cast<const unsigned*>(G + (size_t)y * W + a_lo) + wc);
+      const int c0 = a_lo + 4 * wc;
+      const uint8_t* row = G + (size_t)y * W;
+      unsigned v;
+      if (c0 >= 0 && c0 + 3 < W) {
+        v = __ldg(reinterpret_cast<const unsigned*>(row + c0));
+      } else {
+        v = (unsigned)__ldg(row + reflect101(c0, W)) | ((unsigned)__ldg(row + reflect101(c0 + 1, W)) << 8) |
+            ((unsigned)__ldg(row + reflect101(c0 + 2, W)) << 16) | ((unsigned)__ldg(row + reflect101(c0 + 3, W)) << 24);
+      }
+      reinterpret_cast<unsigned*>(g8)[idx] = v;
     }
   } else {
     for (int idx = tid; idx < NROWS * PITCH; idx += 256) {

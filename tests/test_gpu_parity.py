@@ -327,3 +327,40 @@ def test_fused_flow_histogram_and_host_pipe(torch, ops):
     pf, ph = pipe.flow(torch.from_numpy(clip).pin_memory(), want_flow=True, want_hist=True)
     assert np.array_equal(pf, flow_h) and np.array_equal(ph, fh_h)
     pipe.close()
+
+
+def test_c5_concurrent_streams_mixed_ops(torch, ops):
+    """BASELINE configs[4] in miniature: several concurrent video streams pinned to one GPU
+    (sharding.stream_assignment), each with its own OpticalFlow handle and CUDA stream, mixed
+    flow + histogram work interleaved batch by batch.  Per-stream state must not leak: every
+    stream's results equal those of running that stream alone, bit for bit."""
+    from scannertools_b200 import sharding
+    n_streams, h, w, frames_per_stream, batch = 6, 360, 640, 9, 4
+    mine = sharding.stream_assignment(n_streams * 2, 2)[1]          # the streams "rank 1 of 2" owns
+    assert len(mine) == n_streams
+    clips = {sid: dev(torch, synth.textured_clip(50 + sid, frames_per_stream, h, w)) for sid in mine}
+    # reference: one stream at a time on the default stream
+    solo = ops.OpticalFlow(w, h, max_batch=frames_per_stream - 1)
+    want = {}
+    for sid in mine:
+        flow, fh = solo.execute_with_histogram(clips[sid])
+        want[sid] = (flow.clone(), fh.clone(), ops.histogram(clips[sid]).clone())
+    solo.close()
+    # concurrent: per-stream handles and CUDA streams, batches interleaved across streams
+    handles = {sid: ops.OpticalFlow(w, h, max_batch=batch) for sid in mine}
+    cstreams = {sid: torch.cuda.Stream() for sid in mine}
+    got = {sid: ([], [], []) for sid in mine}
+    torch.cuda.synchronize()
+    for b0 in range(0, frames_per_stream - 1, batch):
+        for sid in mine:
+            b1 = min(b0 + batch, frames_per_stream - 1)
+            with torch.cuda.stream(cstreams[sid]):
+                flow, fh = handles[sid].execute_with_histogram(clips[sid][b0:b1 + 1], stream=cstreams[sid])
+                hist = ops.histogram(clips[sid][b0:b1 + (1 if b1 == frames_per_stream - 1 else 0)], stream=cstreams[sid])
+                got[sid][0].append(flow); got[sid][1].append(fh); got[sid][2].append(hist)
+    torch.cuda.synchronize()
+    for sid in mine:
+        assert torch.equal(torch.cat(got[sid][0]), want[sid][0]), sid
+        assert torch.equal(torch.cat(got[sid][1]), want[sid][1]), sid
+        assert torch.equal(torch.cat(got[sid][2]), want[sid][2]), sid
+        handles[sid].close()
