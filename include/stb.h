@@ -153,6 +153,18 @@ STB_API int stb_resize_target(int frame_w, int frame_h, int width, int height, i
 STB_API int stb_resize_bilinear_u8(const uint8_t* const* d_src, int n, int src_w, int src_h, int channels,
                                    uint8_t* const* d_dst, int dst_w, int dst_h, stb_stream_t stream);
 
+/* ---- ConvertColor -------------------------------------------------------------
+ * Replaces cv::cvtColor on 8-bit frames for the conversions the shipped pipelines use:
+ * COLOR_RGB2HSV (scannertools/old/cpp_ops/imgproc.cpp:41, feeding the HSV histogram of
+ * old/histograms.py:32-36) plus BGR2HSV, RGB2GRAY, BGR2GRAY, RGB<->BGR of
+ * scannertools_cpp/imgproc/convert_color_kernel.cpp:19-25,61; bit-exact with OpenCV's integer
+ * paths.  stb_color_code maps the reference's conversion names ("COLOR_RGB2HSV", ...) to codes
+ * (-1 = not implemented); stb_color_out_channels gives the output channel count. */
+STB_API int stb_color_code(const char* name);
+STB_API int stb_color_out_channels(int code);
+STB_API int stb_convert_color_u8(const uint8_t* const* d_src, int n, int width, int height, int code,
+                                 uint8_t* const* d_dst, stb_stream_t stream);
+
 /* ---- measurement hooks (bench.py) -----------------------------------------------------------
  * stb_launch_count: kernels this library has launched in this process (all entry points).
  * stb_farneback_profile: when enabled, every level-0 pair brackets its fused update-iteration

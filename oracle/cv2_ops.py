@@ -93,3 +93,9 @@ def resize(frame, width, height):
     """Resize op with the default interpolation (scannertools_cpp/imgproc/resize_kernel.cpp:31-35,69-71):
     cv::resize(img, out, Size(width, height), 0, 0, INTER_LINEAR)."""
     return cv2.resize(frame, (width, height), interpolation=cv2.INTER_LINEAR)
+
+
+def convert_color(frame, conversion):
+    """ConvertColor / ConvertToHSVCPP ops: cv::cvtColor(frame, out, <conversion>)
+    (scannertools_cpp/imgproc/convert_color_kernel.cpp:270-276, old/cpp_ops/imgproc.cpp:41)."""
+    return cv2.cvtColor(frame, getattr(cv2, conversion))

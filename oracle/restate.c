@@ -536,3 +536,31 @@ ORC_API void orc_resize_linear_u8(const uint8_t* src, int sw, int sh, int cn, ui
   }
   free(xofs); free(xa);
 }
+
+/* ---- ConvertColor (next row): cv::cvtColor RGB2HSV on 8-bit frames -------------
+ * old/cpp_ops/imgproc.cpp:41.  OpenCV's integer path (hsv_shift = 12, H range 180). */
+ORC_API void orc_rgb2hsv_u8(const uint8_t* rgb, size_t n_px, uint8_t* hsv) {
+  static int sdiv[256], hdiv[256], init = 0;
+  if (!init) {
+    sdiv[0] = hdiv[0] = 0;
+    for (int i = 1; i < 256; ++i) {
+      sdiv[i] = cv_round((255 << 12) / (1. * i));
+      hdiv[i] = cv_round((180 << 12) / (6. * i));
+    }
+    init = 1;
+  }
+  for (size_t i = 0; i < n_px; ++i) {
+    int r = rgb[3 * i], g = rgb[3 * i + 1], b = rgb[3 * i + 2];
+    int v = b > g ? b : g; if (r > v) v = r;
+    int vmin = b < g ? b : g; if (r < vmin) vmin = r;
+    int diff = v - vmin;
+    int vr = v == r ? -1 : 0, vg = v == g ? -1 : 0;
+    int s = (diff * sdiv[v] + (1 << 11)) >> 12;
+    int h = (vr & (g - b)) + (~vr & ((vg & (b - r + 2 * diff)) + ((~vg) & (r - g + 4 * diff))));
+    h = (h * hdiv[diff] + (1 << 11)) >> 12;
+    h += h < 0 ? 180 : 0;
+    hsv[3 * i] = (uint8_t)(h < 0 ? 0 : (h > 255 ? 255 : h));
+    hsv[3 * i + 1] = (uint8_t)s;
+    hsv[3 * i + 2] = (uint8_t)v;
+  }
+}

@@ -130,3 +130,10 @@ def resize(frame, width, height):
     out = np.empty((height, width) + ((cn,) if f.ndim == 3 else ()), np.uint8)
     lib().orc_resize_linear_u8(_p(f), C.c_int(sw), C.c_int(sh), C.c_int(cn), _p(out), C.c_int(width), C.c_int(height))
     return out
+
+
+def rgb2hsv(frame):
+    f = np.ascontiguousarray(frame, np.uint8)
+    out = np.empty_like(f)
+    lib().orc_rgb2hsv_u8(_p(f), C.c_size_t(f.shape[0] * f.shape[1]), _p(out))
+    return out

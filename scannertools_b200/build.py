@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libscannertools_b200.so')
 OBJ = os.path.join(HERE, 'build')
-SOURCES = ['common.cu', 'hist.cu', 'farneback.cu', 'pipe.cu', 'resize.cu']
+SOURCES = ['common.cu', 'hist.cu', 'farneback.cu', 'pipe.cu', 'resize.cu', 'convert_color.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC,-fvisibility=hidden', '-I', os.path.join(ROOT, 'include'), '-I', CSRC]
 
@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
 
 OPS_OUT = os.path.join(HERE, 'libscannertools_imgproc.so')
 OPS_SOURCES = ['histogram_kernel_gpu.cpp', 'optical_flow_kernel_gpu.cpp', 'flow_histogram_kernel_gpu.cpp',
-               'frame_difference_kernel_gpu.cpp', 'resize_kernel_gpu.cpp', 'compat_runtime.cpp']
+               'frame_difference_kernel_gpu.cpp', 'resize_kernel_gpu.cpp', 'convert_color_kernel_gpu.cpp', 'compat_runtime.cpp']
 
 
 def build_scanner_ops(force=False, scanner_include=None):

@@ -197,6 +197,29 @@ def resize(frames, width=0, height=0, min=False, preserve_aspect=False, interpol
     return out
 
 
+def convert_color(frames, conversion='COLOR_RGB2HSV', stream=None):
+    """ConvertColor op (scannertools_cpp/imgproc/convert_color_kernel.cpp:239-281) / ConvertToHSVCPP
+    (old/cpp_ops/imgproc.cpp:14-48) on uint8 RGB frames; bit-exact with cv::cvtColor.  Implemented:
+    COLOR_RGB2HSV, COLOR_BGR2HSV, COLOR_RGB2GRAY, COLOR_BGR2GRAY, COLOR_BGR2RGB, COLOR_RGB2BGR."""
+    torch = _torch()
+    lib = _lib.load()
+    code = lib.stb_color_code(conversion.encode())
+    if code < 0:
+        raise NotImplementedError('ConvertColor: %s is not implemented' % conversion)
+    if isinstance(frames, torch.Tensor) and frames.dim() == 3:
+        frames = frames.unsqueeze(0)
+    lst, H, W = _frames_list(frames, torch.uint8, 'frames', 3)
+    if not lst:
+        raise ValueError('ConvertColor needs at least one frame')
+    oc = lib.stb_color_out_channels(code)
+    out = torch.empty((len(lst), H, W, oc), dtype=torch.uint8, device=lst[0].device)
+    with torch.cuda.device(lst[0].device):
+        st = _lib.ptr_table([f.data_ptr() for f in lst])
+        dt = _lib.ptr_table([out[i].data_ptr() for i in range(len(lst))])
+        _lib.check(lib.stb_convert_color_u8(st, len(lst), W, H, code, dt, _stream_ptr(stream)), lib)
+    return out
+
+
 class OpticalFlow:
     """OpticalFlow op (dense Farneback, the reference's hard-coded parameters).
 

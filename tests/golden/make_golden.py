@@ -78,6 +78,14 @@ def main():
         rs['in_' + name] = img
         rs['out_' + name] = cv2_ops.resize(img, dw, dh)
     np.savez_compressed(os.path.join(HERE, 'resize.npz'), meta=str(meta), **rs)
+    # ConvertColor (next row): the conversions the B200 build implements
+    rng = np.random.default_rng(77)
+    img = rng.integers(0, 256, (60, 107, 3), dtype=np.uint8)
+    img[0, :6] = [[0, 0, 0], [255, 255, 255], [255, 0, 0], [0, 255, 0], [0, 0, 255], [128, 128, 127]]
+    cc = {'in': img}
+    for name in ['COLOR_RGB2HSV', 'COLOR_BGR2HSV', 'COLOR_RGB2GRAY', 'COLOR_BGR2GRAY', 'COLOR_RGB2BGR']:
+        cc[name] = cv2_ops.convert_color(img, name)
+    np.savez_compressed(os.path.join(HERE, 'convert_color.npz'), meta=str(meta), **cc)
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -163,6 +163,20 @@ def test_emu_resize_bit_exact(emu):
     assert emu.stb_resize_bilinear_u8(_lib.ptr_table([0]), 1, 4, 4, 2, _lib.ptr_table([0]), 2, 2, None) != 0   # 2 channels: unsupported
 
 
+def test_emu_convert_color_bit_exact(emu, golden):
+    g = golden('convert_color.npz')
+    img = g['in']
+    h, w = img.shape[:2]
+    for name in ['COLOR_RGB2HSV', 'COLOR_BGR2HSV', 'COLOR_RGB2GRAY', 'COLOR_BGR2GRAY', 'COLOR_RGB2BGR']:
+        code = emu.stb_color_code(name.encode())
+        oc = emu.stb_color_out_channels(code)
+        out = np.zeros((h, w, oc), np.uint8)
+        assert emu.stb_convert_color_u8(_lib.ptr_table([img.ctypes.data]), 1, w, h, code, _lib.ptr_table([out.ctypes.data]), None) == 0
+        assert np.array_equal(out.reshape(g[name].shape), g[name]), name
+    assert emu.stb_color_code(b'COLOR_BGR2XYZ') == -1
+    assert emu.stb_convert_color_u8(_lib.ptr_table([img.ctypes.data]), 1, w, h, 99, _lib.ptr_table([img.ctypes.data]), None) != 0
+
+
 def test_emu_pipe_host_path(emu):
     h, w = 48, 64
     clip = synth.textured_clip(5, 6, h, w)

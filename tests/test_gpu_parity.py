@@ -189,6 +189,24 @@ def test_resize_goldens_and_pipeline_size(torch, ops, golden):
         ops.resize(dev(torch, fr[:1]), width=10, height=10, interpolation='INTER_CUBIC')
 
 
+def test_convert_color_and_hsv_histogram(torch, ops, golden):
+    """ConvertColor (next row, 8f rank 3) and the HSV-histogram pipeline it feeds
+    (compute_hsv_histograms: ConvertToHSVCPP -> Histogram, old/histograms.py:32-36)."""
+    g = golden('convert_color.npz')
+    for name in ['COLOR_RGB2HSV', 'COLOR_BGR2HSV', 'COLOR_RGB2GRAY', 'COLOR_BGR2GRAY', 'COLOR_RGB2BGR']:
+        out = ops.convert_color(dev(torch, g['in']), name).cpu().numpy()[0]
+        assert np.array_equal(out.reshape(g[name].shape), g[name]), name
+    fr = synth.noise_clip(13, 2, 1080, 1920)
+    hsv = ops.convert_color(dev(torch, fr), 'COLOR_RGB2HSV')
+    hsv_h = hsv.cpu().numpy()
+    for i in range(2):
+        assert np.array_equal(hsv_h[i], (cvo.convert_color(fr[i], 'COLOR_RGB2HSV') if cvo else restate.rgb2hsv(fr[i])))
+    hist = ops.histogram(hsv).cpu().numpy()
+    assert np.array_equal(hist[0], o_hist(hsv_h[0]))
+    with pytest.raises(NotImplementedError):
+        ops.convert_color(dev(torch, fr[:1]), 'COLOR_BGR2XYZ')
+
+
 # ------------------------------------------------------------------ OpticalFlow
 FLOW_MEAN_TOL, FLOW_MAX_TOL = 1e-3, 1e-2   # px, north_star
 

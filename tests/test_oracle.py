@@ -75,6 +75,14 @@ def test_restate_resize(golden):
         assert np.array_equal(restate.resize(g['in_' + nme], out.shape[1], out.shape[0]), out), nme
 
 
+def test_restate_rgb2hsv(golden):
+    g = golden('convert_color.npz')
+    assert np.array_equal(restate.rgb2hsv(g['in']), g['COLOR_RGB2HSV'])
+    assert np.array_equal(restate.rgb2hsv(g['in'][..., ::-1]), g['COLOR_BGR2HSV'])
+    assert np.array_equal(restate.gray(g['in']), g['COLOR_BGR2GRAY'])
+    # exhaustive-ish sweep against cv2 when available is in test_cv2_matches_goldens
+
+
 def test_cv2_matches_goldens(golden, have_cv2):
     if not have_cv2:
         pytest.skip('cv2 not importable')
@@ -87,6 +95,11 @@ def test_cv2_matches_goldens(golden, have_cv2):
     assert np.array_equal(cv2_ops.histogram(gh['in_noise_37x53']), gh['out_noise_37x53'])
     gf = golden('flowhist.npz')
     assert np.array_equal(cv2_ops.flow_histogram(gf['in_stress_213x120']), gf['out_stress_213x120'])
+    gc = golden('convert_color.npz')
+    assert np.array_equal(cv2_ops.convert_color(gc['in'], 'COLOR_RGB2HSV'), gc['COLOR_RGB2HSV'])
+    vals = np.arange(0, 256, 5, dtype=np.uint8)
+    grid = np.stack(np.meshgrid(vals, vals, vals, indexing='ij'), -1).reshape(-1, 1, 3)
+    assert np.array_equal(cv2_ops.convert_color(grid, 'COLOR_RGB2HSV'), restate.rgb2hsv(grid))
     gr = golden('resize.npz')
     assert np.array_equal(cv2_ops.resize(gr['in_up'], 200, 100), gr['out_up'])
     gs = golden('shot_c1.npz')

@@ -27,7 +27,7 @@ def test_ops_and_kernels_registered_under_reference_names(shim):
     (histogram_kernel_gpu.cpp:79-82, optical_flow_kernel_cpu.cpp:51-54, optical_flow_kernel_gpu.cpp:109-112,
     flow_histogram_kernel_cpu.cpp:62-67, frame_difference_kernel_cpu.cpp:74-80)."""
     expect = {b'Histogram': (1, 0, 0), b'OpticalFlow': (1, 0, 1), b'FlowHistogram': (1, 0, 0), b'FrameDifference': (0, -1, 0),
-              b'Resize': (1, 0, 0)}
+              b'Resize': (1, 0, 0), b'ConvertColor': (1, 0, 0), b'ConvertToHSVCPP': (1, 0, 0)}
     for op, (batched, lo, hi) in expect.items():
         b, l, h = C.c_int(-1), C.c_int(99), C.c_int(99)
         assert shim.stb_shim_registered(op, C.byref(b), C.byref(l), C.byref(h)) == 1, op
@@ -99,3 +99,20 @@ def test_resize_kernel_class_with_serialized_args(shim):
         assert np.array_equal(got[i], restate.resize(fr[i], ow.value, oh.value))
     bad = _resize_args(width=10, height=10, interpolation=b'INTER_CUBIC')
     assert shim.stb_shim_resize(P(fr), 1, 480, 270, 3, bad, len(bad), P(out), out.size, C.byref(ow), C.byref(oh), 0) == -4
+
+
+@pytest.mark.gpu
+def test_convert_color_kernel_classes(shim):
+    fr = synth.noise_clip(8, 2, 45, 64)
+    out = np.zeros((2, 45, 64, 3), np.uint8)
+    oc = C.c_int()
+    name = b'COLOR_RGB2HSV'
+    args = b'\x0a' + bytes([len(name)]) + name               # ConvertColorArgs{conversion = 1}
+    assert shim.stb_shim_convert_color(P(fr), 2, 64, 45, args, len(args), P(out), C.byref(oc), 0) == 0 and oc.value == 3
+    for i in range(2):
+        assert np.array_equal(out[i], restate.rgb2hsv(fr[i]))
+    out2 = np.zeros_like(out)
+    assert shim.stb_shim_convert_color(P(fr), 2, 64, 45, None, -1, P(out2), C.byref(oc), 0) == 0     # ConvertToHSVCPP
+    assert np.array_equal(out2, out)
+    bad = b'\x0a' + bytes([len(b'COLOR_BGR2XYZ')]) + b'COLOR_BGR2XYZ'
+    assert shim.stb_shim_convert_color(P(fr), 1, 64, 45, bad, len(bad), P(out), C.byref(oc), 0) == -4
