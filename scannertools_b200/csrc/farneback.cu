@@ -181,7 +181,7 @@ pyr_kernel(const uint8_t* __restrict__ gray, float* __restrict__ I, PyrParams p,
 // (1080p, 720p, 640x480 ...).  cv::resize's bilinear taps are then exactly (0.5, 0.5) at source
 // offset S*o + S/2 - 1, so Gaussian + down-sampling collapse into ONE separable FIR of
 // 2r+2 merged taps c[t] = (g[t] + g[t-1]) / 2 evaluated at stride S = 2^K.
-// Tile = 32 x 8 outputs.  The u8 source region is staged in shared memory with aligned 4-byte
+// Tile = 32 x 16 outputs (32 x 8 for K = 3).  The u8 source region is staged in shared memory with aligned 4-byte
 // loads (interior tiles) or per-byte REFLECT_101 (tiles touching the left/right image edge);
 // phase 1 = horizontal FIR at the 32 output columns for every staged row, phase 2 = vertical FIR.
 // ---------------------------------------------------------------------------------------------
@@ -193,7 +193,8 @@ pyr_pow2_kernel(const uint8_t* __restrict__ gray, float* __restrict__ I, int W, 
   constexpr int S = 1 << K;
   constexpr int RAD = (K == 1) ? 1 : (K == 2 ? 4 : 9);
   constexpr int NT = 2 * RAD + 2;
-  constexpr int NROWS = NT + S * 7;
+  constexpr int TH = (K == 3) ? 8 : 16;                      // output rows per tile (K = 3 would need 56 KB of shared memory at 16)
+  constexpr int NROWS = NT + S * (TH - 1);
   constexpr int LEAD = 8 - (RAD + 1 - S / 2);                 // byte offset of the first tap inside the aligned region
   constexpr int PITCH = ((LEAD + NT + S * 31) + 3) & ~3;      // bytes per staged row
   __shared__ __align__(16) uint8_t g8[NROWS * PITCH];
@@ -205,7 +206,7 @@ pyr_pow2_kernel(const uint8_t* __restrict__ gray, float* __restrict__ I, int W, 
   const int frame = frame0 + blockIdx.z;
   const uint8_t* G = gray + (size_t)frame * W * H;
   float* out = I + (size_t)frame * w * h;
-  const int ox0 = blockIdx.x * 32, oy0 = blockIdx.y * 8;
+  const int ox0 = blockIdx.x * 32, oy0 = blockIdx.y * TH;
   const int a_lo = S * ox0 - 8;                                // aligned first staged column
   const int r_lo = S * oy0 + S / 2 - 1 - RAD;                  // first staged row
   if (tid < NT) taps[tid] = mt.c[tid];
@@ -251,13 +252,17 @@ pyr_pow2_kernel(const uint8_t* __restrict__ gray, float* __restrict__ I, int W, 
   }
   __syncthreads();
   {
-    const int ox = tid & 31, oyl = tid >> 5;
-    const int x = ox0 + ox, y = oy0 + oyl;
-    if (x < w && y < h) {
-      float a = 0.f;
+    const int ox = tid & 31;
+    const int x = ox0 + ox;
 #pragma unroll
-      for (int t = 0; t < NT; ++t) a = fmaf(taps[t], hx[S * oyl + t][ox], a);
-      out[(size_t)y * w + x] = a;
+    for (int oyl = tid >> 5; oyl < TH; oyl += 8) {
+      const int y = oy0 + oyl;
+      if (x < w && y < h) {
+        float a = 0.f;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) a = fmaf(taps[t], hx[S * oyl + t][ox], a);
+        out[(size_t)y * w + x] = a;
+      }
     }
   }
 }
@@ -1517,7 +1522,7 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
                      (const uint8_t*)h->gray, h->I, w, hh, pp.taps[0], pp.taps[1], pp.taps[2], fa, (w % 4 == 0) ? 1 : 0);
           STB_CHECK_LAUNCH("pyr0_kernel");
         } else if (h->pow2[k]) {
-          const dim3 g(ceil_div(w, 32), ceil_div(hh, 8), fb - fa);
+          const dim3 g(ceil_div(w, 32), ceil_div(hh, k == 3 ? 8 : 16), fb - fa);
           if (k == 1) stb_launch(pyr_pow2_kernel<1>, g, dim3(256), 0, s, (const uint8_t*)h->gray, h->I, h->W, h->H, h->merged[k], fa);
           else if (k == 2) stb_launch(pyr_pow2_kernel<2>, g, dim3(256), 0, s, (const uint8_t*)h->gray, h->I, h->W, h->H, h->merged[k], fa);
           else stb_launch(pyr_pow2_kernel<3>, g, dim3(256), 0, s, (const uint8_t*)h->gray, h->I, h->W, h->H, h->merged[k], fa);

@@ -34,6 +34,13 @@ __device__ __forceinline__ void flow_bins(float x, float y, int& bm, int& ba) {
 }
 
 
+#ifdef STB_CPU_EMU
+#define STB_NOINLINE __attribute__((noinline))
+#else
+#define STB_NOINLINE __noinline__
+#endif
+static __device__ STB_NOINLINE void flow_bins_exact_slow(float x, float y, int& bm, int& ba) { flow_bins(x, y, bm, ba); }
+
 // Same result as flow_bins, cheaper on average: the bins are first located with approximate
 // (MUFU) reciprocal / rsqrt arithmetic and no double precision; only values that land within
 // a guard band of a bin edge (10x / 7x wider than the approximation error bound: 4e-6 relative
@@ -58,8 +65,8 @@ __device__ __forceinline__ void flow_bins_fast(float x, float y, int& bm, int& b
   if (y < 0.0f) a = 360.0f - a;
   const float t = a * (64.0f / 360.0f);
   exact |= fabsf(t - rintf(t)) <= 1.5e-4f;                               // approximation error <= ~2e-5 bins
-  if (exact) {
-    flow_bins(x, y, bm, ba);
+  if (__builtin_expect(exact, 0)) {
+    flow_bins_exact_slow(x, y, bm, ba);   // rare (< 0.1 % of pixels): kept out of line so the hot path stays small
     return;
   }
   bm = (m < 64.0f) ? (int)m : -1;
