@@ -356,7 +356,6 @@ class Pipe:
         with torch.cuda.device(self.device):
             _lib.check(self._lib.stb_pipe_hist(self._p, C.c_void_p(ptr), n, C.c_void_p(hist.ctypes.data),
                                                C.c_void_p(S.ctypes.data) if scores else None), self._lib)
-        self._keep = frames
         return hist, S
 
     def flow(self, frames, want_flow=True, want_hist=False, flow_out=None):
