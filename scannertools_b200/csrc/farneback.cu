@@ -552,8 +552,48 @@ __device__ __forceinline__ void update_matrices_px(const float* __restrict__ R0,
                     __ldg(R0 + 4 * n + o), R1, n, w, h, x, y, dx, dy, m);
 }
 
+// Two VERTICALLY adjacent pixels (x, y) and (x, y+1) handled by one thread, consecutive lanes on
+// consecutive x.  Their bilinear footprints in R1 almost always share a row (floor(y + dy) of
+// vertical neighbours differs by exactly 1 except at integer crossings), so 3 rows x 2 columns
+// per plane serve both pixels (30 loads instead of 40), and -- unlike a horizontal pair, whose
+// lanes stride by two pixels -- every load of a warp covers one contiguous run of floats: about
+// 1.3 L1 wavefronts per load instead of 3.  Same values and arithmetic as two single calls.
+__device__ __forceinline__ void update_matrices_vpair(const float* __restrict__ R0, const float* __restrict__ R1, int n,
+                                                      int w, int h, int x, int y, float2 fa, float2 fb, float ma[5],
+                                                      float mb[5]) {
+  const int o = y * w + x;
+  float qa[5], qb[5];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) { qa[c] = __ldg(R0 + c * n + o); qb[c] = __ldg(R0 + c * n + o + w); }
+  float fxa = (float)x + fa.x, fya = (float)y + fa.y;
+  float fxb = (float)x + fb.x, fyb = (float)(y + 1) + fb.y;
+  const int x1a = __float2int_rd(fxa), y1a = __float2int_rd(fya);
+  const int x1b = __float2int_rd(fxb), y1b = __float2int_rd(fyb);
+  const bool ina = (unsigned)x1a < (unsigned)(w - 1) && (unsigned)y1a < (unsigned)(h - 1);
+  const bool inb = (unsigned)x1b < (unsigned)(w - 1) && (unsigned)y1b < (unsigned)(h - 1);
+  if (ina && inb && x1b == x1a && y1b == y1a + 1) {
+    fxa -= (float)x1a; fya -= (float)y1a; fxb -= (float)x1b; fyb -= (float)y1b;
+    const float a00 = (1.f - fxa) * (1.f - fya), a01 = fxa * (1.f - fya), a10 = (1.f - fxa) * fya, a11 = fxa * fya;
+    const float b00 = (1.f - fxb) * (1.f - fyb), b01 = fxb * (1.f - fyb), b10 = (1.f - fxb) * fyb, b11 = fxb * fyb;
+    const float* p = R1 + (y1a * w + x1a);
+    float ra[5], rb[5];
+#pragma unroll
+    for (int pl = 0; pl < 5; ++pl) {
+      const float t00 = __ldg(p + pl * n), t01 = __ldg(p + pl * n + 1);
+      const float t10 = __ldg(p + pl * n + w), t11 = __ldg(p + pl * n + w + 1);
+      const float t20 = __ldg(p + pl * n + 2 * w), t21 = __ldg(p + pl * n + 2 * w + 1);
+      ra[pl] = a00 * t00 + a01 * t01 + a10 * t10 + a11 * t11;
+      rb[pl] = b00 * t10 + b01 * t11 + b10 * t20 + b11 * t21;
+    }
+    um_finish(qa[0], qa[1], qa[2], qa[3], qa[4], true, ra[0], ra[1], ra[2], ra[3], ra[4], w, h, x, y, fa.x, fa.y, ma);
+    um_finish(qb[0], qb[1], qb[2], qb[3], qb[4], true, rb[0], rb[1], rb[2], rb[3], rb[4], w, h, x, y + 1, fb.x, fb.y, mb);
+  } else {
+    update_matrices_q(qa[0], qa[1], qa[2], qa[3], qa[4], R1, n, w, h, x, y, fa.x, fa.y, ma);
+    update_matrices_q(qb[0], qb[1], qb[2], qb[3], qb[4], R1, n, w, h, x, y + 1, fb.x, fb.y, mb);
+  }
+}
+
 // initial M of a level from the up-sampled coarser flow (Appendix A.4-5).
-// Two horizontally adjacent pixels per thread (8-byte accesses of R0 / M when w is even).
 __device__ __forceinline__ void upsample_axis(int d, double scale, int n_src, int& s, float& f) {
   if (scale == 0.5) {   // exact halving: (d + 0.5) * 0.5 - 0.5 is exact in float, skip the double path
     f = (float)d * 0.5f - 0.25f;
@@ -582,41 +622,37 @@ __device__ __forceinline__ float2 upsample_flow(const float2* __restrict__ fc, i
 __global__ void __launch_bounds__(256)
 updmat_init_kernel(const float* __restrict__ R, const float* __restrict__ flow_coarse, float* __restrict__ M,
                    int w, int h, int wc, int hc, double scale_x, double scale_y, float flow_mul, int pair0) {
-  const int x = (blockIdx.x * 32 + (threadIdx.x & 31)) * 2;
-  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  // two vertically adjacent pixels per thread, consecutive lanes on consecutive x (see
+  // update_matrices_vpair)
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = (blockIdx.y * 8 + (threadIdx.x >> 5)) * 2;
   if (x >= w || y >= h) return;
   const int pair = pair0 + blockIdx.z;
   const int n = w * h;
-  const bool two = x + 1 < w;
+  const bool two = y + 1 < h;
   float2 da = make_float2(0.f, 0.f), db = make_float2(0.f, 0.f);
   if (flow_coarse != nullptr) {
     const float2* fc = reinterpret_cast<const float2*>(flow_coarse) + (size_t)pair * wc * hc;
     int sy; float fy;
     upsample_axis(y, scale_y, hc, sy, fy);
     da = upsample_flow(fc, wc, hc, sy, fy, x, scale_x, flow_mul);
-    if (two) db = upsample_flow(fc, wc, hc, sy, fy, x + 1, scale_x, flow_mul);
+    if (two) {
+      upsample_axis(y + 1, scale_y, hc, sy, fy);
+      db = upsample_flow(fc, wc, hc, sy, fy, x, scale_x, flow_mul);
+    }
   }
   const float* R0 = R + (size_t)pair * 5 * n;
   const float* R1 = R0 + (size_t)5 * n;
-  const int o = y * w + x;
   float ma[5], mb[5];
-  float* Mo = M + (size_t)pair * 5 * n + o;
-  if (two && (w & 1) == 0) {
-    float2 q[5];
+  float* Mo = M + (size_t)pair * 5 * n + (y * w + x);
+  if (two) {
+    update_matrices_vpair(R0, R1, n, w, h, x, y, da, db, ma, mb);
 #pragma unroll
-    for (int c = 0; c < 5; ++c) q[c] = __ldg(reinterpret_cast<const float2*>(R0 + c * n + o));
-    update_matrices_pair(q, R1, n, w, h, x, y, da, db, ma, mb);
-#pragma unroll
-    for (int c = 0; c < 5; ++c) *reinterpret_cast<float2*>(Mo + c * n) = make_float2(ma[c], mb[c]);
+    for (int c = 0; c < 5; ++c) { Mo[c * n] = ma[c]; Mo[c * n + w] = mb[c]; }
   } else {
     update_matrices_px(R0, R1, n, w, h, x, y, da.x, da.y, ma);
 #pragma unroll
     for (int c = 0; c < 5; ++c) Mo[c * n] = ma[c];
-    if (two) {
-      update_matrices_px(R0, R1, n, w, h, x + 1, y, db.x, db.y, mb);
-#pragma unroll
-      for (int c = 0; c < 5; ++c) Mo[c * n + 1] = mb[c];
-    }
   }
 }
 
@@ -781,21 +817,49 @@ constexpr int kFiGC = 6;                      // output columns per horizontal i
 constexpr int kFiVtWords = kFiRawW * 33;      // one transposed vertical-sum buffer
 constexpr int kFiFlStride = kFiTW + 1;        // float2 row stride of the staged flow (bank spread)
 
-// Global-memory phase shared by both winSize-15 kernels: consecutive threads along x, two adjacent
-// pixels per thread (8-byte accesses of R0 / M' / flow when rows are 8-byte aligned, i.e. w even).
+// Global-memory phase shared by both winSize-15 kernels.
+//   UPDATE: each thread takes two vertically adjacent pixels, consecutive lanes on consecutive x
+//           (update_matrices_vpair): unit-stride R1 gathers with a shared middle row.  Measured on
+//           B200 against the alternatives: one pixel per thread 618 us, two horizontally adjacent
+//           pixels with 8-byte R0 / M' accesses 555 us per 16-pair level-0 launch.
+//   !UPDATE: two horizontally adjacent pixels per thread so the flow goes out as 16-byte stores.
 template <bool UPDATE, bool HIST>
 __device__ __forceinline__ void iter15_global_phase(const float2* fl, unsigned* fh, float* __restrict__ Mout,
                                                     const float* __restrict__ R, const PtrBatch<float>& flow_out,
                                                     int32_t* __restrict__ flow_hist, int w, int h, int pair, int ox0, int oy0) {
   const int tid = threadIdx.x, warp = tid >> 5;
   const size_t n = (size_t)w * h;
-  const float* R0 = R + (size_t)pair * 5 * n;
-  const float* R1 = R0 + 5 * n;
   const int ni = (int)n;
+  if (UPDATE) {
+    const float* R0 = R + (size_t)pair * 5 * n;
+    const float* R1 = R0 + 5 * n;
+    float* Mp = Mout + (size_t)pair * 5 * n;
+#pragma unroll 1
+    for (int i = 0; i < (kFiTW * kFiTH) / (2 * kFiThreads); ++i) {
+      const int p2 = tid + i * kFiThreads;          // vertical pixel-pair index inside the tile
+      const int tp = p2 / kFiTW, tx = p2 - tp * kFiTW;
+      const int x = ox0 + tx, y = oy0 + 2 * tp;
+      if (x >= w || y >= h) continue;
+      const float2 fa = fl[(2 * tp) * kFiFlStride + tx];
+      const float2 fb = fl[(2 * tp + 1) * kFiFlStride + tx];
+      float* Mo = Mp + (y * w + x);
+      float ma[5], mb[5];
+      if (y + 1 < h) {
+        update_matrices_vpair(R0, R1, ni, w, h, x, y, fa, fb, ma, mb);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) { Mo[c * ni] = ma[c]; Mo[c * ni + w] = mb[c]; }
+      } else {
+        update_matrices_px(R0, R1, ni, w, h, x, y, fa.x, fa.y, ma);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) Mo[c * ni] = ma[c];
+      }
+    }
+    return;
+  }
   const bool pair_ok = (w & 1) == 0;
 #pragma unroll 1
   for (int i = 0; i < (kFiTW * kFiTH) / (2 * kFiThreads); ++i) {
-    const int p2 = tid + i * kFiThreads;            // pixel-pair index inside the tile
+    const int p2 = tid + i * kFiThreads;            // horizontal pixel-pair index inside the tile
     const int ty = p2 / (kFiTW / 2), tx = (p2 - ty * (kFiTW / 2)) * 2;
     const int x = ox0 + tx, y = oy0 + ty;
     if (x >= w || y >= h) continue;
@@ -803,47 +867,26 @@ __device__ __forceinline__ void iter15_global_phase(const float2* fl, unsigned* 
     const float2 fb = fl[ty * kFiFlStride + tx + 1];
     const bool two = (x + 1 < w);
     const int o = y * w + x;
-    if (UPDATE) {
-      float ma[5], mb[5];
-      if (two && pair_ok) {
-        float2 q[5];
-#pragma unroll
-        for (int c = 0; c < 5; ++c) q[c] = __ldg(reinterpret_cast<const float2*>(R0 + c * ni + o));
-        update_matrices_pair(q, R1, ni, w, h, x, y, fa, fb, ma, mb);
+    if (flow_out.p[blockIdx.z] != nullptr) {
+      float2* fo = reinterpret_cast<float2*>(flow_out.p[blockIdx.z]) + o;
+      if (two && pair_ok && ((reinterpret_cast<uintptr_t>(fo) & 15u) == 0)) {
+        *reinterpret_cast<float4*>(fo) = make_float4(fa.x, fa.y, fb.x, fb.y);
       } else {
-        update_matrices_px(R0, R1, ni, w, h, x, y, fa.x, fa.y, ma);
-        if (two) update_matrices_px(R0, R1, ni, w, h, x + 1, y, fb.x, fb.y, mb);
+        fo[0] = fa;
+        if (two) fo[1] = fb;
       }
-      float* Mo = Mout + (size_t)pair * 5 * n + o;
-      if (two && pair_ok) {
-#pragma unroll
-        for (int c = 0; c < 5; ++c) *reinterpret_cast<float2*>(Mo + c * ni) = make_float2(ma[c], mb[c]);
-      } else {
-#pragma unroll
-        for (int c = 0; c < 5; ++c) { Mo[c * ni] = ma[c]; if (two) Mo[c * ni + 1] = mb[c]; }
-      }
-    } else {
-      if (flow_out.p[blockIdx.z] != nullptr) {
-        float2* fo = reinterpret_cast<float2*>(flow_out.p[blockIdx.z]) + o;
-        if (two && pair_ok && ((reinterpret_cast<uintptr_t>(fo) & 15u) == 0)) {
-          *reinterpret_cast<float4*>(fo) = make_float4(fa.x, fa.y, fb.x, fb.y);
-        } else {
-          fo[0] = fa;
-          if (two) fo[1] = fb;
-        }
-      }
-      if (HIST) {
-        // fused FlowHistogram (flow_histogram_kernel_cpu.cpp:33-49) of the flow just produced
-        unsigned* my = fh + warp * STB_FLOWHIST_INTS;
-        int bm, ba;
-        flow_bins_fast(fa.x, fa.y, bm, ba);
+    }
+    if (HIST) {
+      // fused FlowHistogram (flow_histogram_kernel_cpu.cpp:33-49) of the flow just produced
+      unsigned* my = fh + warp * STB_FLOWHIST_INTS;
+      int bm, ba;
+      flow_bins_fast(fa.x, fa.y, bm, ba);
+      if (bm >= 0) atomicAdd(my + bm, 1u);
+      if (ba >= 0) atomicAdd(my + 64 + ba, 1u);
+      if (two) {
+        flow_bins_fast(fb.x, fb.y, bm, ba);
         if (bm >= 0) atomicAdd(my + bm, 1u);
         if (ba >= 0) atomicAdd(my + 64 + ba, 1u);
-        if (two) {
-          flow_bins_fast(fb.x, fb.y, bm, ba);
-          if (bm >= 0) atomicAdd(my + bm, 1u);
-          if (ba >= 0) atomicAdd(my + 64 + ba, 1u);
-        }
       }
     }
   }
@@ -1539,7 +1582,7 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
         frames_done = fb;
       }
       (void)F;
-      stb_launch(updmat_init_kernel, dim3(ceil_div(w, 64), ceil_div(hh, 8), np), dim3(256), 0, s, (const float*)h->R,
+      stb_launch(updmat_init_kernel, dim3(ceil_div(w, 32), ceil_div(hh, 16), np), dim3(256), 0, s, (const float*)h->R,
                  coarse, h->M[0], w, hh, wc, hc, up_sx, up_sy, (float)(1. / h->prm.pyr_scale), p0);
       STB_CHECK_LAUNCH("updmat_init_kernel");
       if (dbg && h->dbg_pair >= p0 && h->dbg_pair < p1) {
