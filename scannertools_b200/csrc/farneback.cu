@@ -619,40 +619,47 @@ __device__ __forceinline__ float2 upsample_flow(const float2* __restrict__ fc, i
   return make_float2((h0x * ay0 + h1x * fy) * flow_mul, (h0y * ay0 + h1y * fy) * flow_mul);
 }
 
+// Two horizontally adjacent pixels per thread (8-byte accesses of R0 / M when w is even).  This
+// kernel is DRAM-bound (69 % of peak): the vertical-pair mapping that helps the L1-bound iteration
+// kernel measured 12 % slower here (495 vs 440 us per 16-pair level-0 launch).
 __global__ void __launch_bounds__(256)
 updmat_init_kernel(const float* __restrict__ R, const float* __restrict__ flow_coarse, float* __restrict__ M,
                    int w, int h, int wc, int hc, double scale_x, double scale_y, float flow_mul, int pair0) {
-  // two vertically adjacent pixels per thread, consecutive lanes on consecutive x (see
-  // update_matrices_vpair)
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y = (blockIdx.y * 8 + (threadIdx.x >> 5)) * 2;
+  const int x = (blockIdx.x * 32 + (threadIdx.x & 31)) * 2;
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= w || y >= h) return;
   const int pair = pair0 + blockIdx.z;
   const int n = w * h;
-  const bool two = y + 1 < h;
+  const bool two = x + 1 < w;
   float2 da = make_float2(0.f, 0.f), db = make_float2(0.f, 0.f);
   if (flow_coarse != nullptr) {
     const float2* fc = reinterpret_cast<const float2*>(flow_coarse) + (size_t)pair * wc * hc;
     int sy; float fy;
     upsample_axis(y, scale_y, hc, sy, fy);
     da = upsample_flow(fc, wc, hc, sy, fy, x, scale_x, flow_mul);
-    if (two) {
-      upsample_axis(y + 1, scale_y, hc, sy, fy);
-      db = upsample_flow(fc, wc, hc, sy, fy, x, scale_x, flow_mul);
-    }
+    if (two) db = upsample_flow(fc, wc, hc, sy, fy, x + 1, scale_x, flow_mul);
   }
   const float* R0 = R + (size_t)pair * 5 * n;
   const float* R1 = R0 + (size_t)5 * n;
+  const int o = y * w + x;
   float ma[5], mb[5];
-  float* Mo = M + (size_t)pair * 5 * n + (y * w + x);
-  if (two) {
-    update_matrices_vpair(R0, R1, n, w, h, x, y, da, db, ma, mb);
+  float* Mo = M + (size_t)pair * 5 * n + o;
+  if (two && (w & 1) == 0) {
+    float2 q[5];
 #pragma unroll
-    for (int c = 0; c < 5; ++c) { Mo[c * n] = ma[c]; Mo[c * n + w] = mb[c]; }
+    for (int c = 0; c < 5; ++c) q[c] = __ldg(reinterpret_cast<const float2*>(R0 + c * n + o));
+    update_matrices_pair(q, R1, n, w, h, x, y, da, db, ma, mb);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) *reinterpret_cast<float2*>(Mo + c * n) = make_float2(ma[c], mb[c]);
   } else {
     update_matrices_px(R0, R1, n, w, h, x, y, da.x, da.y, ma);
 #pragma unroll
     for (int c = 0; c < 5; ++c) Mo[c * n] = ma[c];
+    if (two) {
+      update_matrices_px(R0, R1, n, w, h, x + 1, y, db.x, db.y, mb);
+#pragma unroll
+      for (int c = 0; c < 5; ++c) Mo[c * n + 1] = mb[c];
+    }
   }
 }
 
@@ -1582,7 +1589,7 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
         frames_done = fb;
       }
       (void)F;
-      stb_launch(updmat_init_kernel, dim3(ceil_div(w, 32), ceil_div(hh, 16), np), dim3(256), 0, s, (const float*)h->R,
+      stb_launch(updmat_init_kernel, dim3(ceil_div(w, 64), ceil_div(hh, 8), np), dim3(256), 0, s, (const float*)h->R,
                  coarse, h->M[0], w, hh, wc, hc, up_sx, up_sy, (float)(1. / h->prm.pyr_scale), p0);
       STB_CHECK_LAUNCH("updmat_init_kernel");
       if (dbg && h->dbg_pair >= p0 && h->dbg_pair < p1) {
