@@ -44,7 +44,7 @@ def main():
         by = 16 * (8 * 1080 * 1920 + 512)
         print('flowhist 1080p n=16: %.3f ms %.0f fps %.1f GB/s %.1f%%' % (t * 1e3, 16 / t, by / t / 1e9, 100 * by / t / PEAK))
     if 'flow' in which:
-        for (h, w, n, bytes_per) in [(480, 640, 16, 114336000), (720, 1280, 8, 343008000), (1080, 1920, 8, 771768000)]:
+        for (h, w, n, bytes_per) in [(480, 640, 16, 114336000), (480, 640, 64, 114336000), (720, 1280, 8, 343008000), (720, 1280, 32, 343008000), (1080, 1920, 8, 771768000), (1080, 1920, 16, 771768000)]:
             base = synth.textured_clip(1, 4, h, w)
             clip = np.concatenate([base] * ((n + 1 + 3) // 4))[:n + 1]
             fr = torch.from_numpy(clip).cuda()
