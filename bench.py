@@ -327,9 +327,9 @@ def run_ours(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of iter15_tma_kernel<true,false> at level 0 from the
-# committed `ncu --set full` capture (profiles/r01_ncu_full_table.txt: grid (40,34,16), 1.981 GB read
-# + 660 MB written for the 16 pairs of one launch), per PAIR; scaled by the pairs a bench launch processes.
-NCU_TRAFFIC_BYTES_PER_PAIR = (1.981e9 + 660.4e6) / 16
+# committed `ncu --set full` capture (profiles/r01_ncu_full_table.txt: grid (40,34,16), 1.980 GB read
+# + 646 MB written for the 16 pairs of one launch), per PAIR; scaled by the pairs a bench launch processes.
+NCU_TRAFFIC_BYTES_PER_PAIR = (1.980e9 + 646.0e6) / 16
 
 
 def extra_workloads(torch, ops, lib, args):

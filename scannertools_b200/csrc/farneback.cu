@@ -332,7 +332,7 @@ constexpr int kPeRows = 8 + 2 * kPolyN;       // 18 input rows per vertical item
 // memory (coalesced along x, replicate clamp), results r0,r1,r2 go to shared memory row-major.
 // Horizontal pass: item = (row, 4 adjacent columns): 16-byte shared loads of a 20-float window
 // per component, 11-tap sums in registers, float4 stores of the 5 output planes.
-__global__ void __launch_bounds__(kPeThreads, 3)
+__global__ void __launch_bounds__(kPeThreads, 4)
 polyexp_kernel(const float* __restrict__ I, float* __restrict__ R, int w, int h, PolyConsts c, int frame0) {
   __shared__ __align__(16) float V[3][kPeTH][kPeStride];
   const int tid = threadIdx.x;

@@ -382,3 +382,32 @@ def test_c5_concurrent_streams_mixed_ops(torch, ops):
         assert torch.equal(torch.cat(got[sid][1]), want[sid][1]), sid
         assert torch.equal(torch.cat(got[sid][2]), want[sid][2]), sid
         handles[sid].close()
+
+
+def test_c_abi_error_behaviour_on_device(torch, ops):
+    """Errors are status codes + stb_last_error(), never exceptions across the C boundary and
+    never a silent fallback (SURVEY 8b 'Errors')."""
+    import ctypes as C
+    from scannertools_b200 import _lib
+    lib = _lib.load()
+    of = ops.OpticalFlow(160, 120, max_batch=2)
+    fr = dev(torch, synth.textured_clip(1, 4, 120, 160))
+    out = torch.empty((3, 120, 160, 2), dtype=torch.float32, device='cuda')
+    ft = _lib.ptr_table([fr[i].data_ptr() for i in range(4)])
+    ot = _lib.ptr_table([out[i].data_ptr() for i in range(3)])
+    rc = lib.stb_farneback_run(of._h, ft, 3, ot, None)            # 3 pairs > max_batch 2
+    assert rc == -1 and b'max_pairs' in lib.stb_last_error()
+    bad = _lib.ptr_table([fr[0].data_ptr(), 0, fr[2].data_ptr()])
+    assert lib.stb_farneback_run(of._h, bad, 2, ot, None) == -1 and b'NULL' in lib.stb_last_error()
+    assert lib.stb_farneback_run(of._h, ft, 0, ot, None) == 0    # empty batch is a no-op
+    assert lib.stb_hist_rgb16_strided(C.c_void_p(fr.data_ptr()), 10, 2, 160, 120, C.c_void_p(out.data_ptr()), None) == -1  # stride < frame
+    prm = _lib.FarnebackParams(3, 0.5, 0, 15, 3, 7, 1.2, 0)       # poly_n = 7: not implemented
+    h = C.c_void_p()
+    assert lib.stb_farneback_create(160, 120, 1, C.byref(prm), C.byref(h)) == -4 and not h.value
+    pipe = ops.Pipe(160, 120, max_batch=2, want_flow=False)
+    with pytest.raises(_lib.StbError):
+        pipe.flow(synth.textured_clip(1, 3, 120, 160), want_flow=True)
+    pipe.close()
+    of.close()
+    with pytest.raises(TypeError):
+        ops.histogram(torch.zeros((1, 4, 4, 3), dtype=torch.uint8))      # host tensor: not a device frame
