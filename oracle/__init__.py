@@ -11,6 +11,14 @@ Two layers:
     restatement, pinned against goldens produced by `cv2_ops`
     (tests/golden/, generator script committed beside them).
 
-Parity status: the reference's own tests hold no golden vectors for this path
-(SURVEY.md §4, §8c); parity is pinned to OpenCV itself via cv2 4.13.0.
+Parity status, precisely:
+  * The reference's own tests hold NO golden vectors for this path, and its
+    C++ wrappers cannot be compiled or run here (they need the Scanner engine and OpenCV C++).
+  * What IS pinned: (1) the arithmetic, against outputs of OpenCV itself (the un-vendored
+    dependency that implements it) produced here through cv2 4.13.0 with the wrappers' exact call
+    arguments -- tests/golden/*.npz; (2) the one Python op on the path, ShotBoundaries, against
+    outputs of the REFERENCE ITSELF: scannertools/shot_detection.py imported from /root/reference
+    behind a scannerpy stub (tests/golden/ref_import.py) -> tests/golden/shot_reference.npz.
+  * What is not pinned by anything the reference ships: the C++ wrappers' behaviour beyond what
+    their source shows (argument order, output layout), e.g. OpenCV-version drift.
 """

@@ -10,6 +10,7 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), '..', '..'))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import cv2  # noqa: E402
 from oracle import cv2_ops  # noqa: E402
 from scannertools_b200 import synth  # noqa: E402
@@ -86,6 +87,28 @@ def main():
     for name in ['COLOR_RGB2HSV', 'COLOR_BGR2HSV', 'COLOR_RGB2GRAY', 'COLOR_BGR2GRAY', 'COLOR_RGB2BGR']:
         cc[name] = cv2_ops.convert_color(img, name)
     np.savez_compressed(os.path.join(HERE, 'convert_color.npz'), meta=str(meta), **cc)
+    # ShotBoundaries goldens from the REFERENCE ITSELF (its Python op imported from /root/reference
+    # behind a scannerpy stub, ref_import.py): histogram sequences -> boundary lists
+    import ref_import
+    if ref_import.available():
+        sd, ty = ref_import.load('shot_detection'), ref_import.load('types')
+        rng = np.random.default_rng(2024)
+
+        def make(n, n_cuts, jitter):
+            base = rng.integers(0, 20000, size=(n_cuts + 1, 3, 16))
+            cuts_ = np.sort(rng.choice(np.arange(1, max(n, 2)), size=min(n_cuts, max(n - 1, 0)), replace=False)) if n > 1 else np.array([], int)
+            seg = np.searchsorted(cuts_, np.arange(n), side='right')
+            h = base[seg] + rng.integers(-jitter, jitter + 1, size=(n, 3, 16))
+            return np.clip(h, 0, None).astype(np.int32)
+        cases = {}
+        for name, (n, k, j) in {'n1': (1, 0, 5), 'n2': (2, 1, 5), 'n40': (40, 3, 50), 'n600': (600, 5, 200),
+                                'n1300': (1300, 9, 400), 'flat300': (300, 0, 0), 'noisy900': (900, 4, 6000)}.items():
+            h = make(n, k, j)
+            rows = sd.shot_boundaries(None, [ty.histograms(x.tobytes(), None) for x in h])
+            cases['hist_' + name] = h
+            cases['bounds_' + name] = np.array(rows[0], np.int32)
+        np.savez_compressed(os.path.join(HERE, 'shot_reference.npz'),
+                            meta='generated by the reference scannertools/shot_detection.py::shot_boundaries', **cases)
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -66,6 +66,32 @@ def test_restate_frame_difference(golden):
     assert np.array_equal(restate.frame_difference(g['prev'], g['cur']), g['out'])
 
 
+def test_shot_boundaries_against_the_reference_itself(golden, have_cv2):
+    """tests/golden/shot_reference.npz was produced by the reference's OWN Python op
+    (scannertools/shot_detection.py imported from /root/reference behind a scannerpy stub): the
+    oracle's restatement and the product's host logic must reproduce it exactly; when the reference
+    tree is present (build container) the op is also re-run live."""
+    import os
+    import sys
+    from scannertools_b200 import shot_detection, types
+    g = golden('shot_reference.npz')
+    names = [k[5:] for k in g.files if k.startswith('hist_')]
+    assert len(names) == 7
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    import ref_import
+    live = ref_import.load('shot_detection') if ref_import.available() else None
+    for nme in names:
+        h, want = g['hist_' + nme], list(g['bounds_' + nme])
+        elems = [types.histograms(types.histogram_bytes(x)) for x in h]
+        assert shot_detection.shot_boundaries(None, elems)[0] == want, nme                 # product host logic
+        assert shot_detection.shot_boundaries(None, scores=restate.shot_scores(h))[0] == want, nme   # via C scores
+        if have_cv2:
+            from oracle import cv2_ops
+            assert cv2_ops.shot_boundaries(list(h)) == want, nme                           # oracle restatement
+        if live is not None:
+            assert live.shot_boundaries(None, elems)[0] == want, nme                       # the reference, live
+
+
 def test_restate_resize(golden):
     g = golden('resize.npz')
     names = [k[3:] for k in g.files if k.startswith('in_')]
