@@ -166,9 +166,14 @@ int stb_pipe_flow(stb_pipe* p, const uint8_t* h_frames, int n, float* h_flow, in
   std::vector<float*> fl((size_t)B);
   int c = 0, prev_m = 0;
   for (int p0 = 0; p0 < n; ++c) {
-    // The first upload of a call cannot overlap any compute: keep it short (a quarter batch),
-    // then full batches whose upload hides behind the previous batch's kernels.
-    const int cap = (c == 0 && n > B) ? (B >= 4 ? B / 4 : 1) : B;
+    // The first upload of a call cannot overlap any compute, and batch c+1's upload only hides
+    // behind batch c's kernels if batch c is not much smaller: start at an eighth of a batch and
+    // double (B/8, B/4, B/2, B, B, ...), so the exposed copy time is one small upload.
+    int cap = B;
+    if (n > B && c < 3) {
+      cap = B >> (3 - c);
+      if (cap < 1) cap = 1;
+    }
     const int m = n - p0 < cap ? n - p0 : cap;
     const int slot = c & 1;
     STB_CUDA(cudaStreamWaitEvent(p->s_copy, p->comp_done[slot], 0));
