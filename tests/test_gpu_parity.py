@@ -277,9 +277,11 @@ def test_farneback_stage_by_stage(torch, ops):
     of.close()
 
 
-@pytest.mark.parametrize('h,w,seed', [(480, 640, 1), (240, 426, 7), (720, 1280, 2), (1080, 1920, 3)])
+@pytest.mark.parametrize('h,w,seed', [(480, 640, 1), (240, 426, 7), (720, 1280, 2), (1080, 1920, 3), (2160, 3840, 4), (270, 478, 5)])
 def test_farneback_parity_sizes(torch, ops, h, w, seed):
-    """C2 (640x480) and the other BASELINE resolutions; 426x240 runs 3 scales only."""
+    """C2 (640x480) and the other BASELINE resolutions; 426x240 runs 3 scales only; 4K is the
+    largest frame of the BASELINE configs; 478x270 has rows that are not 16-byte aligned (the LDG
+    fall-back of the iteration kernel and the generic pyramid kernel)."""
     clip = synth.textured_clip(seed, 3, h, w)
     of = ops.OpticalFlow(w, h, max_batch=2)
     out = of.execute(dev(torch, clip)).cpu().numpy()
