@@ -189,6 +189,13 @@ STB_API int stb_pipe_destroy(stb_pipe* p);
 STB_API int stb_pipe_hist(stb_pipe* p, const uint8_t* h_frames, int n, int32_t* h_hist, int32_t* h_S);
 /* n+1 frames -> n flow frames (h_flow may be NULL) and/or n*128 flow histograms (may be NULL) */
 STB_API int stb_pipe_flow(stb_pipe* p, const uint8_t* h_frames, int n, float* h_flow, int32_t* h_flow_hist);
+/* Asynchronous form: enqueues the whole call and returns a ticket (0 or 1; -1 when n == 0); the host
+ * buffers must stay valid and untouched until stb_pipe_wait(ticket).  At most two calls may be in
+ * flight; the second call's uploads overlap the first call's kernels, so a stream of calls keeps
+ * the GPU busy without the per-call start-up bubble. */
+STB_API int stb_pipe_flow_async(stb_pipe* p, const uint8_t* h_frames, int n, float* h_flow, int32_t* h_flow_hist,
+                                int* ticket);
+STB_API int stb_pipe_wait(stb_pipe* p, int ticket);
 
 #ifdef __cplusplus
 }

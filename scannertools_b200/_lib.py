@@ -54,6 +54,8 @@ SIGNATURES = {
     'stb_pipe_destroy': (C.c_int, [_vp]),
     'stb_pipe_hist': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     'stb_pipe_flow': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
+    'stb_pipe_flow_async': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.POINTER(C.c_int)]),
+    'stb_pipe_wait': (C.c_int, [_vp, C.c_int]),
 }
 
 

@@ -17,6 +17,8 @@ struct stb_pipe {
   size_t frame_bytes;
   cudaStream_t s_copy, s_comp, s_out;
   cudaEvent_t copied[2], comp_done[2], out_done[2];
+  cudaEvent_t call_done[2];   // completion of the two most recent asynchronous calls
+  long long calls;            // asynchronous calls submitted so far
   uint8_t* d_frames[2];   // [B+1] frames each
   float* d_flow[2];       // [B] flow frames each (only when flow frames are returned)
   int32_t* d_res;         // per-frame results for the whole call (hist or flow-hist)
@@ -72,6 +74,7 @@ int stb_pipe_create(int width, int height, int max_batch, int want_flow, stb_pip
     e = cudaEventCreateWithFlags(&p->copied[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->comp_done[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->out_done[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->call_done[i], cudaEventDisableTiming);
   }
   if (e != cudaSuccess) {
     int rc = cuda_fail(e, "stb_pipe_create");
@@ -98,6 +101,7 @@ int stb_pipe_destroy(stb_pipe* p) {
     if (p->copied[i]) cudaEventDestroy(p->copied[i]);
     if (p->comp_done[i]) cudaEventDestroy(p->comp_done[i]);
     if (p->out_done[i]) cudaEventDestroy(p->out_done[i]);
+    if (p->call_done[i]) cudaEventDestroy(p->call_done[i]);
   }
   if (p->d_res) cudaFree(p->d_res);
   if (p->d_S) cudaFree(p->d_S);
@@ -144,11 +148,19 @@ int stb_pipe_hist(stb_pipe* p, const uint8_t* h_frames, int n, int32_t* h_hist, 
   return STB_OK;
 }
 
-int stb_pipe_flow(stb_pipe* p, const uint8_t* h_frames, int n, float* h_flow, int32_t* h_flow_hist) {
+int stb_pipe_flow_async(stb_pipe* p, const uint8_t* h_frames, int n, float* h_flow, int32_t* h_flow_hist, int* ticket) {
+  if (ticket) *ticket = -1;
   if (!p || n < 0 || (n > 0 && !h_frames)) { set_error("stb_pipe_flow: invalid argument"); return STB_ERR_INVALID; }
   if (!p->fb) { set_error("stb_pipe_flow: pipe was created with want_flow = 0"); return STB_ERR_INVALID; }
   if (n == 0) return STB_OK;
   if (!h_flow && !h_flow_hist) { set_error("stb_pipe_flow: no output requested"); return STB_ERR_INVALID; }
+  // is the previous asynchronous call still running?  (then its kernels hide this call's first upload)
+  const bool idle = p->calls == 0 || cudaEventQuery(p->call_done[(p->calls - 1) & 1]) == cudaSuccess;
+  (void)cudaGetLastError();
+  if ((size_t)n > p->res_cap_frames) {   // growing the result buffers must not race with pending work
+    STB_CUDA(cudaStreamSynchronize(p->s_comp));
+    STB_CUDA(cudaStreamSynchronize(p->s_out));
+  }
   int rc = ensure_results(p, (size_t)n);
   if (rc) return rc;
   const size_t fbytes = p->frame_bytes;
@@ -170,7 +182,7 @@ int stb_pipe_flow(stb_pipe* p, const uint8_t* h_frames, int n, float* h_flow, in
     // behind batch c's kernels if batch c is not much smaller: start at an eighth of a batch and
     // double (B/8, B/4, B/2, B, B, ...), so the exposed copy time is one small upload.
     int cap = B;
-    if (n > B && c < 3) {
+    if (idle && n > B && c < 3) {
       cap = B >> (3 - c);
       if (cap < 1) cap = 1;
     }
@@ -215,9 +227,25 @@ int stb_pipe_flow(stb_pipe* p, const uint8_t* h_frames, int n, float* h_flow, in
   }
   if (h_flow_hist)
     STB_CUDA(cudaMemcpyAsync(h_flow_hist, p->d_res, (size_t)n * STB_FLOWHIST_INTS * sizeof(int32_t), cudaMemcpyDeviceToHost, p->s_comp));
-  STB_CUDA(cudaStreamSynchronize(p->s_comp));
-  if (h_flow) STB_CUDA(cudaStreamSynchronize(p->s_out));
+  if (h_flow) STB_CUDA(cudaStreamWaitEvent(p->s_comp, p->out_done[(c - 1) & 1], 0));   // join the flow read-back stream
+  const int t = (int)(p->calls & 1);
+  STB_CUDA(cudaEventRecord(p->call_done[t], p->s_comp));
+  p->calls++;
+  if (ticket) *ticket = t;
   return STB_OK;
+}
+
+int stb_pipe_wait(stb_pipe* p, int ticket) {
+  if (!p || ticket < 0 || ticket > 1) { set_error("stb_pipe_wait: invalid argument"); return STB_ERR_INVALID; }
+  STB_CUDA(cudaEventSynchronize(p->call_done[ticket]));
+  return STB_OK;
+}
+
+int stb_pipe_flow(stb_pipe* p, const uint8_t* h_frames, int n, float* h_flow, int32_t* h_flow_hist) {
+  int ticket = -1;
+  int rc = stb_pipe_flow_async(p, h_frames, n, h_flow, h_flow_hist, &ticket);
+  if (rc || ticket < 0) return rc;
+  return stb_pipe_wait(p, ticket);
 }
 
 }  // extern "C"

@@ -358,6 +358,26 @@ class Pipe:
                                                C.c_void_p(S.ctypes.data) if scores else None), self._lib)
         return hist, S
 
+    def flow_async(self, frames, hist_out):
+        """Asynchronous OpticalFlow -> FlowHistogram: enqueues the call and returns a ticket for
+        `wait`.  `frames` (host, ideally pinned) and `hist_out` (int32 [n,2,64] numpy or pinned
+        tensor) must stay untouched until then.  Two calls may be in flight: submit call i+1, then
+        wait for call i, and the uploads of one call hide behind the kernels of the other."""
+        torch = _torch()
+        ptr, shape = self._host_ptr(frames)
+        n = shape[0] - 1
+        optr, oshape = self._host_ptr(hist_out)
+        if int(np.prod(oshape)) != n * 2 * FLOW_HIST_BINS:
+            raise ValueError('hist_out must hold n x 2 x 64 int32')
+        t = C.c_int(-1)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.stb_pipe_flow_async(self._p, C.c_void_p(ptr), n, None, C.c_void_p(optr), C.byref(t)), self._lib)
+        return t.value
+
+    def wait(self, ticket):
+        if ticket >= 0:
+            _lib.check(self._lib.stb_pipe_wait(self._p, ticket), self._lib)
+
     def flow(self, frames, want_flow=True, want_hist=False, flow_out=None):
         """frames: host uint8 [n+1,H,W,3] -> (float32 [n,H,W,2] or None, int32 [n,2,64] or None)."""
         torch = _torch()

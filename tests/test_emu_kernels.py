@@ -198,4 +198,13 @@ def test_emu_pipe_host_path(emu):
     assert emu.stb_pipe_flow(p, P(clip), 5, None, P(fh_only)) == 0
     assert np.array_equal(fh_only, fh)
     assert emu.stb_pipe_flow(p, P(clip), 5, None, None) != 0
+    # asynchronous form: two calls in flight, tickets alternate
+    r0, r1 = np.zeros((5, 128), np.int32), np.zeros((5, 128), np.int32)
+    t0, t1 = C.c_int(-1), C.c_int(-1)
+    assert emu.stb_pipe_flow_async(p, P(clip), 5, None, P(r0), C.byref(t0)) == 0
+    assert emu.stb_pipe_flow_async(p, P(clip), 5, None, P(r1), C.byref(t1)) == 0
+    assert {t0.value, t1.value} == {0, 1}
+    assert emu.stb_pipe_wait(p, t0.value) == 0 and emu.stb_pipe_wait(p, t1.value) == 0
+    assert np.array_equal(r0, fh) and np.array_equal(r1, fh)
+    assert emu.stb_pipe_wait(p, 7) != 0
     emu.stb_pipe_destroy(p)

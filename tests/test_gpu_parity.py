@@ -346,6 +346,13 @@ def test_fused_flow_histogram_and_host_pipe(torch, ops):
     pipe = ops.Pipe(w, h, max_batch=2, want_flow=True)       # batches of 2 pairs -> 3 batches with halo reuse
     pf, ph = pipe.flow(torch.from_numpy(clip).pin_memory(), want_flow=True, want_hist=True)
     assert np.array_equal(pf, flow_h) and np.array_equal(ph, fh_h)
+    # asynchronous form, two calls in flight on pinned buffers
+    pinned = torch.from_numpy(clip).pin_memory()
+    res = [torch.zeros((5, 2, 64), dtype=torch.int32).pin_memory() for _ in range(2)]
+    t0 = pipe.flow_async(pinned, res[0])
+    t1 = pipe.flow_async(pinned, res[1])
+    pipe.wait(t0); pipe.wait(t1)
+    assert np.array_equal(res[0].numpy(), fh_h) and np.array_equal(res[1].numpy(), fh_h)
     pipe.close()
 
 
