@@ -420,3 +420,23 @@ def test_c_abi_error_behaviour_on_device(torch, ops):
     of.close()
     with pytest.raises(TypeError):
         ops.histogram(torch.zeros((1, 4, 4, 3), dtype=torch.uint8))      # host tensor: not a device frame
+
+
+def test_gray_entry_point_and_pointer_table_paths(torch, ops):
+    """stb_farneback_run_gray (the cv::FarnebackOpticalFlow::calc contract on gray frames) equals
+    the RGB entry point fed the same frames; FlowHistogram through the pointer-table entry point
+    (separate flow buffers) equals the strided one."""
+    h, w = 120, 160
+    clip = synth.textured_clip(12, 4, h, w)
+    of = ops.OpticalFlow(w, h, max_batch=3)
+    rgb_flow = of.execute(dev(torch, clip)).cpu().numpy()
+    gray = np.stack([restate.gray(f) for f in clip])[..., None]
+    gray_flow = of.execute(dev(torch, gray), gray=True).cpu().numpy()
+    assert np.array_equal(rgb_flow, gray_flow)
+    of.close()
+    flows = dev(torch, rgb_flow)
+    a = ops.flow_histogram(flows).cpu().numpy()
+    b = ops.flow_histogram([flows[i].clone() for i in range(3)]).cpu().numpy()
+    assert np.array_equal(a, b)
+    for i in range(3):
+        assert np.array_equal(a[i], restate.flow_histogram(rgb_flow[i]))
