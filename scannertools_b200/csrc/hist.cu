@@ -7,6 +7,8 @@
 // per block.
 //
 // Reference call sites replaced: see include/stb.h.
+#include <cstdlib>
+
 #include "stb_rt.h"
 #include "flow_bins.cuh"
 
@@ -81,7 +83,15 @@ __device__ __forceinline__ void hist_count_vec(const uint4& q, hist_addr_t c0, h
 
 template <class Addr>
 __global__ void __launch_bounds__(kHistThreads, 3)
-hist_rgb16_kernel(Addr addr, unsigned long long nbytes, int32_t* __restrict__ out) {
+hist_rgb16_kernel(Addr addr, unsigned long long nbytes, int32_t* __restrict__ out, unsigned base_blocks, unsigned rem) {
+  // 1-D grid over (frame, part): the first `rem` frames get base_blocks + 1 blocks, the others
+  // base_blocks, so a batch fills the resident wave exactly whatever the frame count
+  unsigned frame, part, nparts;
+  {
+    const unsigned b = blockIdx.x, big = rem * (base_blocks + 1u);
+    if (b < big) { frame = b / (base_blocks + 1u); part = b - frame * (base_blocks + 1u); nparts = base_blocks + 1u; }
+    else { const unsigned bb = b - big; frame = rem + bb / base_blocks; part = bb - (bb / base_blocks) * base_blocks; nparts = base_blocks; }
+  }
   STB_DYN_SMEM(unsigned char, dyn);
   const hist_addr_t origin = hist_origin(dyn);
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -91,14 +101,14 @@ hist_rgb16_kernel(Addr addr, unsigned long long nbytes, int32_t* __restrict__ ou
   }
   __syncthreads();
 
-  const uint8_t* f = addr(blockIdx.y);
+  const uint8_t* f = addr(frame);
   unsigned long long head = (16u - (unsigned)(reinterpret_cast<uintptr_t>(f) & 15u)) & 15u;
   if (head > nbytes) head = nbytes;
   const uint4* v = reinterpret_cast<const uint4*>(f + head);
   const unsigned long long nvec = (nbytes - head) >> 4;
 
-  const unsigned gt = blockIdx.x * kHistThreads + tid;
-  const unsigned long long T = (unsigned long long)gridDim.x * kHistThreads;
+  const unsigned gt = part * kHistThreads + tid;
+  const unsigned long long T = (unsigned long long)nparts * kHistThreads;
   const unsigned ph = (unsigned)((head + gt) % 3u);
   const hist_addr_t wbase = origin + warp * (3u * 2048u) + lane * 4u;
   const hist_addr_t c0 = wbase + ((ph + 0u) % 3u) * 2048u;
@@ -128,7 +138,7 @@ hist_rgb16_kernel(Addr addr, unsigned long long nbytes, int32_t* __restrict__ ou
     hist_count_vec(q, c0, c1, c2);
   }
   // ragged ends (unaligned base pointer / byte count not a multiple of 16): at most 30 bytes
-  if (blockIdx.x == 0) {
+  if (part == 0) {
     const unsigned long long tail0 = head + (nvec << 4);
     const unsigned long long ntail = nbytes - tail0;
     if (tid < head + ntail) {
@@ -139,17 +149,17 @@ hist_rgb16_kernel(Addr addr, unsigned long long nbytes, int32_t* __restrict__ ou
   __syncthreads();
 
   // block reduce: 8 threads per bin (bin = ch*16 + b), each sums 4 lanes x 12 warps
-  const unsigned bin = tid >> 3, part = tid & 7u;
+  const unsigned bin = tid >> 3, rpart = tid & 7u;
   unsigned s = 0;
 #pragma unroll
   for (int w = 0; w < kHistWarps; ++w) {
-    const uint4 q = *reinterpret_cast<const uint4*>(hist_ptr(origin, ((w * STB_HIST_INTS + bin) * 32 + part * 4) * 4));
+    const uint4 q = *reinterpret_cast<const uint4*>(hist_ptr(origin, ((w * STB_HIST_INTS + bin) * 32 + rpart * 4) * 4));
     s += q.x + q.y + q.z + q.w;
   }
   s += __shfl_xor_sync(0xffffffffu, s, 1);
   s += __shfl_xor_sync(0xffffffffu, s, 2);
   s += __shfl_xor_sync(0xffffffffu, s, 4);
-  if (part == 0 && s != 0) atomicAdd(out + (size_t)blockIdx.y * STB_HIST_INTS + bin, (int)s);
+  if (rpart == 0 && s != 0) atomicAdd(out + (size_t)frame * STB_HIST_INTS + bin, (int)s);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -322,14 +332,20 @@ static int launch_hist(Addr addr, int n, unsigned long long nbytes, int32_t* d_o
   // one resident wave (3 blocks/SM) spread over the frames of this launch; never more blocks
   // than there are 4-vector iterations of work
   const int wave = num_sms() * 3;
-  // blocks per frame: fill one resident wave without spilling a handful of blocks into a second
-  // one (448 blocks on 444 slots costs ~25%); with more frames than slots, one block per frame.
-  long long bpf = wave / n;
+  // Total blocks: one resident wave (3 blocks/SM) split over the frames as evenly as possible
+  // (some frames get one block more); spilling a handful of blocks into a second wave costs ~25 %,
+  // leaving slots empty costs proportionally (n = 32 on 444 slots: 416 blocks 66.8 %, 444 blocks ~71 %).
+  // Never more blocks per frame than there are 4-vector iterations of work; with more frames than
+  // slots, one block per frame.
   const long long max_useful = (long long)((nvec + (unsigned long long)kHistThreads * 4 - 1) / ((unsigned long long)kHistThreads * 4));
-  if (bpf > max_useful) bpf = max_useful;
-  if (bpf < 1) bpf = 1;
-  stb_launch(hist_rgb16_kernel<Addr>, dim3((unsigned)bpf, (unsigned)n), dim3(kHistThreads),
-             kHistSmemBytes, s, addr, nbytes, d_out);
+  long long total = wave;
+  if (const char* env = getenv("STB_HIST_WAVES")) { const int k = atoi(env); if (k >= 1 && k <= 16) total = (long long)wave * k; }
+  if (total < n) total = n;
+  if (max_useful >= 1 && total > max_useful * n) total = max_useful * n;
+  if (total < n) total = n;
+  const unsigned base_blocks = (unsigned)(total / n), rem = (unsigned)(total % n);
+  stb_launch(hist_rgb16_kernel<Addr>, dim3((unsigned)total), dim3(kHistThreads), kHistSmemBytes, s, addr, nbytes, d_out,
+             base_blocks, rem);
   STB_CHECK_LAUNCH("hist_rgb16_kernel");
   return STB_OK;
 }
