@@ -220,7 +220,14 @@ __device__ __forceinline__ void flow_count(unsigned* my, float x, float y) {
 
 template <class Addr>
 __global__ void __launch_bounds__(kFlowHistThreads, 3)
-flow_hist_kernel(Addr addr, unsigned long long npx, int32_t* __restrict__ out) {
+flow_hist_kernel(Addr addr, unsigned long long npx, int32_t* __restrict__ out, unsigned base_blocks, unsigned rem) {
+  // 1-D grid over (frame, part), as in hist_rgb16_kernel
+  unsigned frame, part, nparts;
+  {
+    const unsigned b = blockIdx.x, big = rem * (base_blocks + 1u);
+    if (b < big) { frame = b / (base_blocks + 1u); part = b - frame * (base_blocks + 1u); nparts = base_blocks + 1u; }
+    else { const unsigned bb = b - big; frame = rem + bb / base_blocks; part = bb - (bb / base_blocks) * base_blocks; nparts = base_blocks; }
+  }
   STB_DYN_SMEM(unsigned, sh);
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   {
@@ -228,10 +235,10 @@ flow_hist_kernel(Addr addr, unsigned long long npx, int32_t* __restrict__ out) {
     for (unsigned i = tid; i < kFlowHistSmemWords / 4; i += kFlowHistThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();
-  const float* f = addr(blockIdx.y);
+  const float* f = addr(frame);
   unsigned* my = sh + warp * (64 * 32) + lane;
-  const unsigned long long gt = (unsigned long long)blockIdx.x * kFlowHistThreads + tid;
-  const unsigned long long T = (unsigned long long)gridDim.x * kFlowHistThreads;
+  const unsigned long long gt = (unsigned long long)part * kFlowHistThreads + tid;
+  const unsigned long long T = (unsigned long long)nparts * kFlowHistThreads;
   if ((reinterpret_cast<uintptr_t>(f) & 15u) == 0) {
     const float4* v = reinterpret_cast<const float4*>(f);
     const unsigned long long nvec = npx >> 1;
@@ -255,13 +262,13 @@ flow_hist_kernel(Addr addr, unsigned long long npx, int32_t* __restrict__ out) {
   }
   __syncthreads();
   // reduce: 2 threads per bin, each sums 16 lanes x 8 warps of its 16-bit half
-  const unsigned bin = tid >> 1, part = tid & 1u;
+  const unsigned bin = tid >> 1, rpart = tid & 1u;
   const unsigned word = (bin < 64 ? (bin >> 1) : 32 + ((bin - 64) >> 1));
   const unsigned shift = (bin & 1u) * 16u;
   unsigned s = 0;
 #pragma unroll
   for (int w = 0; w < kFlowHistWarps; ++w) {
-    const unsigned* row = sh + (w * 64 + word) * 32 + part * 16;
+    const unsigned* row = sh + (w * 64 + word) * 32 + rpart * 16;
 #pragma unroll
     for (int l = 0; l < 16; l += 4) {
       const uint4 q = *reinterpret_cast<const uint4*>(row + l);
@@ -269,7 +276,7 @@ flow_hist_kernel(Addr addr, unsigned long long npx, int32_t* __restrict__ out) {
     }
   }
   s += __shfl_xor_sync(0xffffffffu, s, 1);
-  if (part == 0 && s != 0) atomicAdd(out + (size_t)blockIdx.y * STB_FLOWHIST_INTS + bin, (int)s);
+  if (rpart == 0 && s != 0) atomicAdd(out + (size_t)frame * STB_FLOWHIST_INTS + bin, (int)s);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -360,15 +367,16 @@ static int launch_flow_hist(Addr addr, int n, unsigned long long npx, int32_t* d
     attr_done[dev] = true;
   }
   const int wave = num_sms() * 3;
-  long long bpf = wave / n;
   const long long max_useful = (long long)((npx / 2 + (unsigned long long)kFlowHistThreads * 2 - 1) / ((unsigned long long)kFlowHistThreads * 2));
   const long long min_needed = (long long)((npx + (unsigned long long)kFlowHistThreads * kFlowHistMaxPxPerThread - 1) /
                                            ((unsigned long long)kFlowHistThreads * kFlowHistMaxPxPerThread));
-  if (bpf > max_useful) bpf = max_useful;
-  if (bpf < min_needed) bpf = min_needed;
-  if (bpf < 1) bpf = 1;
-  stb_launch(flow_hist_kernel<Addr>, dim3((unsigned)bpf, (unsigned)n), dim3(kFlowHistThreads),
-             kFlowHistSmemWords * sizeof(unsigned), s, addr, npx, d_out);
+  long long total = wave;                       // one resident wave, split unevenly over the frames
+  if (max_useful >= 1 && total > max_useful * n) total = max_useful * n;
+  if (total < min_needed * n) total = min_needed * n;   // 16-bit counters: bounded pixels per thread
+  if (total < n) total = n;
+  const unsigned base_blocks = (unsigned)(total / n), rem = (unsigned)(total % n);
+  stb_launch(flow_hist_kernel<Addr>, dim3((unsigned)total), dim3(kFlowHistThreads), kFlowHistSmemWords * sizeof(unsigned), s,
+             addr, npx, d_out, base_blocks, rem);
   STB_CHECK_LAUNCH("flow_hist_kernel");
   return STB_OK;
 }
