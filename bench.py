@@ -396,6 +396,27 @@ def extra_workloads(torch, ops, lib, args):
                       'value': n480 / t, 'unit': 'frames/s', 'ms_per_step': t * 1e3,
                       'roofline': {'bound': 'hbm', 'achieved': n480 * FLOW480_BYTES / t / 1e9, 'peak': peak, 'unit': 'GB/s',
                                    'frac': n480 * FLOW480_BYTES / t / 1e9 / peak}}
+    # C5 in miniature: 8 concurrent 720p streams pinned to this GPU (sharding.stream_assignment puts
+    # 8 of the 64 streams on each of 8 GPUs), each with its own OpticalFlow handle (per-stream state
+    # never crosses streams), mixed OpticalFlow+FlowHistogram and RGB Histogram work, round-robin
+    C5_BYTES = 343008000 + 8 * 1280 * 720 + 512 + 2764992      # flow + flow histogram + RGB histogram per 720p frame
+    n_streams, fps_batch = 8, 16
+    clips = [torch.from_numpy(synth.textured_clip(300 + sidx, fps_batch + 1, 720, 1280)).cuda() for sidx in range(n_streams)]
+    handles = [ops.OpticalFlow(1280, 720, max_batch=fps_batch) for _ in range(n_streams)]
+
+    def c5_step():
+        for sidx in range(n_streams):
+            handles[sidx].execute_with_histogram(clips[sidx], want_flow=False)
+            ops.histogram(clips[sidx][:fps_batch])
+    t = time_dev(c5_step, 5, warm=2)
+    for hnd in handles:
+        hnd.close()
+    frames = n_streams * fps_batch
+    out['c5_mixed_720p'] = {'workload': 'C5 per-GPU share: %d concurrent 1280x720 streams, OpticalFlow+FlowHistogram and RGB Histogram, '
+                                        '%d frames per stream per step' % (n_streams, fps_batch),
+                            'value': frames / t, 'unit': 'frames/s', 'ms_per_step': t * 1e3,
+                            'roofline': {'bound': 'hbm', 'achieved': frames * C5_BYTES / t / 1e9, 'peak': peak, 'unit': 'GB/s',
+                                         'frac': frames * C5_BYTES / t / 1e9 / peak}}
     return out
 
 
