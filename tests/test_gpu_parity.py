@@ -440,3 +440,18 @@ def test_gray_entry_point_and_pointer_table_paths(torch, ops):
     assert np.array_equal(a, b)
     for i in range(3):
         assert np.array_equal(a[i], restate.flow_histogram(rgb_flow[i]))
+
+
+def test_farneback_more_pairs_than_one_pointer_table(torch, ops):
+    """70 pairs in one call: the per-level launches are chunked at the 64-entry pointer table;
+    frames shared by two chunks must get their pyramid / polynomial expansion exactly once."""
+    h, w, n = 64, 96, 70
+    clip = synth.textured_clip(21, n + 1, h, w, max_shift=1.5)
+    of = ops.OpticalFlow(w, h, max_batch=n)
+    out = of.execute(dev(torch, clip)).cpu().numpy()
+    of1 = ops.OpticalFlow(w, h, max_batch=1)
+    for i in (0, 31, 63, 64, 69):
+        single = of1.execute(dev(torch, clip[i:i + 2])).cpu().numpy()[0]
+        assert np.array_equal(out[i], single), i
+        check_flow(out[i], o_flow(clip[i], clip[i + 1]), i)
+    of.close(); of1.close()
