@@ -177,6 +177,24 @@ def test_emu_convert_color_bit_exact(emu, golden):
     assert emu.stb_convert_color_u8(_lib.ptr_table([img.ctypes.data]), 1, w, h, 99, _lib.ptr_table([img.ctypes.data]), None) != 0
 
 
+@pytest.mark.parametrize('levels,iters,win', [(0, 1, 15), (1, 1, 15), (2, 4, 15), (3, 3, 5)])
+def test_emu_farneback_parameter_combinations(emu, levels, iters, win):
+    """stb_farneback_params other than the reference's defaults: fewer pyramid levels, a single
+    iteration (only the last-iteration kernel runs), more iterations, another window."""
+    h, w = 96, 128
+    clip = synth.textured_clip(9, 2, h, w)
+    prm = _lib.FarnebackParams(levels, 0.5, 0, win, iters, 5, 1.2, 0)
+    hd = C.c_void_p()
+    assert emu.stb_farneback_create(w, h, 1, C.byref(prm), C.byref(hd)) == 0
+    out = np.zeros((h, w, 2), np.float32)
+    assert emu.stb_farneback_run(hd, _lib.ptr_table([f.ctypes.data for f in clip]), 1,
+                                 _lib.ptr_table([out.ctypes.data]), None) == 0
+    emu.stb_farneback_destroy(hd)
+    ref = restate.farneback(restate.gray(clip[0]), restate.gray(clip[1]), winsize=win, iters=iters, levels=levels)
+    e = epe(out, ref)
+    assert e.max() < 1e-4, (levels, iters, win, e.max())
+
+
 def test_emu_pipe_host_path(emu):
     h, w = 48, 64
     clip = synth.textured_clip(5, 6, h, w)
