@@ -382,6 +382,15 @@ def extra_workloads(torch, ops, lib, args):
                                   'frac': n4k * HIST4K_BYTES / t / 1e9 / peak},
                      'e2e': {'value': n4k / te, 'unit': 'frames/s', 'h2d_bytes_per_step': n4k * 3840 * 2160 * 3,
                              'd2h_bytes_per_step': n4k * 196}}
+    # HSV variant of the shot-detection histogram (old/histograms.py:32-36): fused ConvertToHSV ->
+    # Histogram against the two-op chain (ConvertColor writes the HSV frame, Histogram reads it back)
+    th = time_dev(lambda: ops.shot_scores(ops.histogram(fr, hsv='COLOR_RGB2HSV')), 10)
+    t2 = time_dev(lambda: ops.shot_scores(ops.histogram(ops.convert_color(fr, 'COLOR_RGB2HSV'))), 3, warm=1)
+    out['hsvhist4k'] = {'workload': '3840x2160 fused RGB->HSV + histogram (16 bins/channel) + shot scores, 32 frames/step, i.i.d. noise',
+                        'value': n4k / th, 'unit': 'frames/s', 'ms_per_step': th * 1e3,
+                        'roofline': {'bound': 'hbm', 'achieved': n4k * HIST4K_BYTES / th / 1e9, 'peak': peak, 'unit': 'GB/s',
+                                     'frac': n4k * HIST4K_BYTES / th / 1e9 / peak},
+                        'unfused_two_op_frames_per_s': n4k / t2}
     del fr, host4k
     # C2: 640x480 Farneback, 16 pairs per step
     from scannertools_b200 import synth

@@ -165,6 +165,18 @@ STB_API int stb_color_out_channels(int code);
 STB_API int stb_convert_color_u8(const uint8_t* const* d_src, int n, int width, int height, int code,
                                  uint8_t* const* d_dst, stb_stream_t stream);
 
+/* ---- fused ConvertToHSV -> Histogram -------------------------------------------
+ * The HSV variant of the shot-detection histogram: scannertools/old/histograms.py:32-36 chains
+ * ConvertToHSVCPP (old/cpp_ops/imgproc.cpp:14-48, cv::cvtColor COLOR_RGB2HSV) into the Histogram
+ * op (histogram_kernel_cpu.cpp:16-46).  One pass over the RGB bytes, the HSV frame is never
+ * materialised; d_out[n][3][16] = histogram of (H, S, V), identical to
+ * stb_hist_rgb16(stb_convert_color_u8(frame, code)).  H < 180, so H bins 12..15 are zero.
+ * code = stb_color_code("COLOR_RGB2HSV") or ("COLOR_BGR2HSV"); anything else is STB_ERR_UNSUPPORTED. */
+STB_API int stb_hist_hsv16(const uint8_t* const* d_frames, int n, int width, int height, int code,
+                           int32_t* d_out, stb_stream_t stream);
+STB_API int stb_hist_hsv16_strided(const uint8_t* d_base, size_t stride_bytes, int n, int width, int height,
+                                   int code, int32_t* d_out, stb_stream_t stream);
+
 /* ---- measurement hooks (bench.py) -----------------------------------------------------------
  * stb_launch_count: kernels this library has launched in this process (all entry points).
  * stb_farneback_profile: when enabled, every level-0 pair brackets its fused update-iteration

@@ -8,19 +8,15 @@
 //   GRAY: (c0*k0 + c1*k1 + c2*k2 + 16384) >> 15 with the 15-bit coefficients {3735,19235,9798}
 //        in B,G,R order.
 #include "stb_rt.h"
+#include "hsv.cuh"
 
 namespace stb {
 
 enum { kCodeRGB2HSV = 0, kCodeBGR2HSV = 1, kCodeRGB2GRAY = 2, kCodeBGR2GRAY = 3, kCodeSwapRB = 4 };
 
 __device__ __forceinline__ void hsv_px(int r, int g, int b, const int* sdiv, const int* hdiv, unsigned char* o) {
-  const int v = max(max(b, g), r), vmin = min(min(b, g), r);
-  const int diff = v - vmin;
-  const int vr = (v == r) ? -1 : 0, vg = (v == g) ? -1 : 0;
-  const int s = (diff * sdiv[v] + (1 << 11)) >> 12;
-  int h = (vr & (g - b)) + (~vr & ((vg & (b - r + 2 * diff)) + ((~vg) & (r - g + 4 * diff))));
-  h = (h * hdiv[diff] + (1 << 11)) >> 12;
-  h += h < 0 ? 180 : 0;
+  int h, s, v;
+  hsv_vals(r, g, b, sdiv, hdiv, h, s, v);
   o[0] = (unsigned char)min(max(h, 0), 255);
   o[1] = (unsigned char)s;
   o[2] = (unsigned char)v;
@@ -30,10 +26,7 @@ __global__ void __launch_bounds__(256)
 convert_color_kernel(PtrBatch<const uint8_t> srcs, PtrBatch<uint8_t> dsts, unsigned long long npx, int code) {
   __shared__ int sdiv[256], hdiv[256];
   if (code <= kCodeBGR2HSV) {
-    const int i = threadIdx.x;
-    // cvRound of an exact double quotient: round half to even
-    sdiv[i] = i ? __double2int_rn((double)(255 << 12) / (double)i) : 0;
-    hdiv[i] = i ? __double2int_rn((double)(180 << 12) / (6.0 * (double)i)) : 0;
+    hsv_tables_init(sdiv, hdiv, threadIdx.x);
     __syncthreads();
   }
   const uint8_t* src = srcs.p[blockIdx.y];

@@ -69,11 +69,20 @@ def _frames_list(frames, dtype, what, last):
     return lst, 0, 0
 
 
-def histogram(frames, stream=None):
+def histogram(frames, stream=None, hsv=None):
     """Histogram op: n RGB24 frames -> int32 [n, 3, 16] (192 B per frame, channel-major, the
-    layout `types.histograms` parses).  Bit-exact with the reference (bin = byte >> 4)."""
+    layout `types.histograms` parses).  Bit-exact with the reference (bin = byte >> 4).
+
+    hsv='COLOR_RGB2HSV' (or 'COLOR_BGR2HSV') gives the HSV variant of the shot-detection
+    histogram (scannertools/old/histograms.py:32-36: ConvertToHSVCPP -> Histogram) in one fused
+    pass, identical to histogram(convert_color(frames, hsv))."""
     torch = _torch()
     lib = _lib.load()
+    code = None
+    if hsv is not None:
+        code = lib.stb_color_code(hsv.encode())
+        if code < 0 or hsv not in ('COLOR_RGB2HSV', 'COLOR_BGR2HSV'):
+            raise ValueError('histogram: hsv must be COLOR_RGB2HSV or COLOR_BGR2HSV, got %r' % (hsv,))
     if isinstance(frames, torch.Tensor) and frames.dim() == 4 and frames.shape[0] > 0:
         # one contiguous batch (a decoder batch / block buffer): strided entry point, one launch
         _require_cuda(frames, torch.uint8, 'frames')
@@ -82,8 +91,13 @@ def histogram(frames, stream=None):
             raise ValueError('frames: expected 3 channels, got %d' % c)
         out = torch.empty((n, 3, HIST_BINS), dtype=torch.int32, device=frames.device)
         with torch.cuda.device(frames.device):
-            _lib.check(lib.stb_hist_rgb16_strided(C.c_void_p(frames.data_ptr()), H * W * 3, n, W, H,
-                                                  C.c_void_p(out.data_ptr()), _stream_ptr(stream)), lib)
+            if code is None:
+                rc = lib.stb_hist_rgb16_strided(C.c_void_p(frames.data_ptr()), H * W * 3, n, W, H,
+                                                C.c_void_p(out.data_ptr()), _stream_ptr(stream))
+            else:
+                rc = lib.stb_hist_hsv16_strided(C.c_void_p(frames.data_ptr()), H * W * 3, n, W, H, code,
+                                                C.c_void_p(out.data_ptr()), _stream_ptr(stream))
+            _lib.check(rc, lib)
         return out
     lst, H, W = _frames_list(frames, torch.uint8, 'frames', 3)
     n = len(lst)
@@ -93,7 +107,11 @@ def histogram(frames, stream=None):
         return out
     with torch.cuda.device(dev):
         tab = _lib.ptr_table([f.data_ptr() for f in lst])
-        _lib.check(lib.stb_hist_rgb16(tab, n, W, H, C.c_void_p(out.data_ptr()), _stream_ptr(stream)), lib)
+        if code is None:
+            rc = lib.stb_hist_rgb16(tab, n, W, H, C.c_void_p(out.data_ptr()), _stream_ptr(stream))
+        else:
+            rc = lib.stb_hist_hsv16(tab, n, W, H, code, C.c_void_p(out.data_ptr()), _stream_ptr(stream))
+        _lib.check(rc, lib)
     return out
 
 

@@ -177,6 +177,35 @@ def test_emu_convert_color_bit_exact(emu, golden):
     assert emu.stb_convert_color_u8(_lib.ptr_table([img.ctypes.data]), 1, w, h, 99, _lib.ptr_table([img.ctypes.data]), None) != 0
 
 
+def test_emu_fused_hsv_histogram(emu, golden):
+    """stb_hist_hsv16 == Histogram(ConvertToHSV(frame)) (old/histograms.py:32-36), incl. ragged pixel
+    counts, unaligned frame bases, BGR input and saturated / grey pixels."""
+    rng = np.random.default_rng(21)
+    rgb, bgr = emu.stb_color_code(b'COLOR_RGB2HSV'), emu.stb_color_code(b'COLOR_BGR2HSV')
+    g = golden('convert_color.npz')
+    cases = [np.ascontiguousarray(g['in']), rng.integers(0, 256, (21, 33, 3), dtype=np.uint8),
+             rng.integers(0, 256, (1, 5, 3), dtype=np.uint8), np.full((40, 64, 3), 255, np.uint8),
+             np.repeat(rng.integers(0, 256, (32, 48, 1), dtype=np.uint8), 3, axis=2)]
+    for img in cases:
+        h, w = img.shape[:2]
+        for code, src in ((rgb, img), (bgr, np.ascontiguousarray(img[..., ::-1]))):
+            out = np.zeros((1, 48), np.int32)
+            assert emu.stb_hist_hsv16(_lib.ptr_table([src.ctypes.data]), 1, w, h, code, P(out), None) == 0
+            ref = restate.histogram(restate.rgb2hsv(img)).reshape(-1)
+            assert np.array_equal(out[0], ref), (img.shape, code)
+            assert out[0].sum() == 3 * w * h and not out[0, 12:16].any()
+    # two frames carved out of one buffer at a 1-byte offset: the unaligned path, strided entry point
+    fr = rng.integers(0, 256, (2, 17, 23, 3), dtype=np.uint8)
+    buf = np.zeros(fr.size + 16, np.uint8)
+    buf[1:1 + fr.size] = fr.reshape(-1)
+    out = np.zeros((2, 48), np.int32)
+    assert emu.stb_hist_hsv16_strided(C.c_void_p(buf.ctypes.data + 1), fr[0].size, 2, 23, 17, rgb, P(out), None) == 0
+    for i in range(2):
+        assert np.array_equal(out[i], restate.histogram(restate.rgb2hsv(fr[i])).reshape(-1))
+    assert emu.stb_hist_hsv16(None, 0, 4, 4, rgb, None, None) == 0
+    assert emu.stb_hist_hsv16(_lib.ptr_table([fr.ctypes.data]), 1, 23, 17, emu.stb_color_code(b'COLOR_RGB2GRAY'), P(out), None) != 0
+
+
 @pytest.mark.parametrize('levels,iters,win', [(0, 1, 15), (1, 1, 15), (2, 4, 15), (3, 3, 5)])
 def test_emu_farneback_parameter_combinations(emu, levels, iters, win):
     """stb_farneback_params other than the reference's defaults: fewer pyramid levels, a single

@@ -203,6 +203,19 @@ def test_convert_color_and_hsv_histogram(torch, ops, golden):
         assert np.array_equal(hsv_h[i], (cvo.convert_color(fr[i], 'COLOR_RGB2HSV') if cvo else restate.rgb2hsv(fr[i])))
     hist = ops.histogram(hsv).cpu().numpy()
     assert np.array_equal(hist[0], o_hist(hsv_h[0]))
+    # fused ConvertToHSV -> Histogram: same counts without materialising the HSV frame
+    fused = ops.histogram(dev(torch, fr), hsv='COLOR_RGB2HSV').cpu().numpy()
+    assert np.array_equal(fused, hist)
+    fused_list = ops.histogram([dev(torch, f) for f in fr], hsv='COLOR_RGB2HSV').cpu().numpy()
+    assert np.array_equal(fused_list, hist)
+    bgr = ops.histogram(dev(torch, np.ascontiguousarray(fr[..., ::-1])), hsv='COLOR_BGR2HSV').cpu().numpy()
+    assert np.array_equal(bgr, hist)
+    clip = synth.cut_clip(5, 70, 90, 161)[0]           # > 64 frames, odd size: unaligned frame bases
+    ref = np.stack([o_hist(cvo.convert_color(f, 'COLOR_RGB2HSV') if cvo else restate.rgb2hsv(f)) for f in clip])
+    assert np.array_equal(ops.histogram(dev(torch, clip), hsv='COLOR_RGB2HSV').cpu().numpy(), ref)
+    assert np.array_equal(ops.histogram([dev(torch, f) for f in clip], hsv='COLOR_RGB2HSV').cpu().numpy(), ref)
+    with pytest.raises(ValueError):
+        ops.histogram(dev(torch, fr[:1]), hsv='COLOR_RGB2GRAY')
     with pytest.raises(NotImplementedError):
         ops.convert_color(dev(torch, fr[:1]), 'COLOR_BGR2XYZ')
 
