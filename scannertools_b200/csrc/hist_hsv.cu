@@ -37,23 +37,73 @@ __device__ __forceinline__ int hsv_byte(unsigned w, int k) {
 #endif
 }
 
+// Counter / table addressing.  On the device both are 32-bit shared-window addresses, so one
+// counter update is SHF (bin) + LEA (base + bin*128) + RED; the emulator uses plain pointers.
+#ifdef STB_CPU_EMU
+struct HsvSmem {
+  unsigned* my;          // this lane's column of this warp's planes
+  const int* sdiv;
+  const int* hdiv;
+  template <int SHIFT>
+  __device__ __forceinline__ void inc(int plane, int x) const { atomicAdd(my + (plane + (x >> SHIFT)) * 32, 1u); }
+  __device__ __forceinline__ int s_div(int v) const { return sdiv[v]; }
+  __device__ __forceinline__ int h_div(int d) const { return hdiv[d]; }
+};
+__device__ __forceinline__ HsvSmem hsv_smem(unsigned* sh, unsigned warp, unsigned lane, const int* sdiv, const int* hdiv) {
+  return HsvSmem{sh + warp * (kHsvPlanes * 32) + lane, sdiv, hdiv};
+}
+#else
+struct HsvSmem {
+  unsigned my, sdiv, hdiv;   // shared-window byte addresses
+  // x >> SHIFT selects the bin (x >= 0).  The shift is opaque to the compiler so that it stays
+  // SHF + LEA instead of being rewritten into shift-left / mask / add.
+  template <int SHIFT>
+  __device__ __forceinline__ void inc(int plane, int x) const {
+    unsigned bin;
+    asm("shr.u32 %0, %1, %2;" : "=r"(bin) : "r"((unsigned)x), "n"(SHIFT));
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(my + (unsigned)plane * 128u + (bin << 7)) : "memory");
+  }
+  __device__ __forceinline__ int s_div(int v) const {
+    int r;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(r) : "r"(sdiv + ((unsigned)v << 2)));
+    return r;
+  }
+  __device__ __forceinline__ int h_div(int d) const {
+    int r;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(r) : "r"(hdiv + ((unsigned)d << 2)));
+    return r;
+  }
+};
+__device__ __forceinline__ HsvSmem hsv_smem(unsigned* sh, unsigned warp, unsigned lane, const int* sdiv, const int* hdiv) {
+  const unsigned base = (unsigned)__cvta_generic_to_shared(sh);
+  return HsvSmem{base + (warp * (kHsvPlanes * 32) + lane) * 4u, (unsigned)__cvta_generic_to_shared(sdiv),
+                 (unsigned)__cvta_generic_to_shared(hdiv)};
+}
+#endif
+
 template <bool SWAP>
-__device__ __forceinline__ void hsv_count_px(unsigned* my, const int* sdiv, const int* hdiv, int c0, int c1, int c2) {
-  int h, s, v;
-  if (SWAP) hsv_vals(c2, c1, c0, sdiv, hdiv, h, s, v);   // BGR input
-  else hsv_vals(c0, c1, c2, sdiv, hdiv, h, s, v);        // RGB input
-  atomicAdd(my + (h >> 4) * 32, 1u);
-  atomicAdd(my + (kHsvPlaneS + (s >> 4)) * 32, 1u);
-  atomicAdd(my + (kHsvPlaneV + (v >> 4)) * 32, 1u);
+__device__ __forceinline__ void hsv_count_px(const HsvSmem& m, int c0, int c1, int c2) {
+  const int r = SWAP ? c2 : c0, g = c1, b = SWAP ? c0 : c2;   // SWAP: BGR input
+  // hsv_vals (hsv.cuh) with the two table reads going through m
+  const int v = max(max(b, g), r), vmin = min(min(b, g), r);
+  const int diff = v - vmin;
+  const int vr = (v == r) ? -1 : 0, vg = (v == g) ? -1 : 0;
+  const int s4096 = diff * m.s_div(v) + (1 << 11);             // s = s4096 >> 12, its bin = s4096 >> 16
+  int h = (vr & (g - b)) + (~vr & ((vg & (b - r + 2 * diff)) + ((~vg) & (r - g + 4 * diff))));
+  h = (h * m.h_div(diff) + (1 << 11)) >> 12;
+  h += h < 0 ? 180 : 0;
+  m.inc<4>(0, h);
+  m.inc<16>(kHsvPlaneS, s4096);
+  m.inc<4>(kHsvPlaneV, v);
 }
 
 // 16 pixels held in twelve 32-bit words
 template <bool SWAP>
-__device__ __forceinline__ void hsv_count_group(unsigned* my, const int* sdiv, const int* hdiv, const unsigned (&w)[12]) {
+__device__ __forceinline__ void hsv_count_group(const HsvSmem& m, const unsigned (&w)[12]) {
 #pragma unroll
   for (int j = 0; j < kHsvGroupPx; ++j) {
     const int b = 3 * j;
-    hsv_count_px<SWAP>(my, sdiv, hdiv, hsv_byte(w[b >> 2], b & 3), hsv_byte(w[(b + 1) >> 2], (b + 1) & 3),
+    hsv_count_px<SWAP>(m, hsv_byte(w[b >> 2], b & 3), hsv_byte(w[(b + 1) >> 2], (b + 1) & 3),
                        hsv_byte(w[(b + 2) >> 2], (b + 2) & 3));
   }
 }
@@ -96,7 +146,7 @@ hist_hsv16_kernel(Addr addr, unsigned long long npx, int32_t* __restrict__ out, 
 
   const uint8_t* f = addr(frame);
   const bool aligned = (reinterpret_cast<uintptr_t>(f) & 15u) == 0;
-  unsigned* my = sh + warp * (kHsvPlanes * 32) + lane;
+  const HsvSmem m = hsv_smem(sh, warp, lane, sdiv, hdiv);
   const unsigned long long ngroups = npx / kHsvGroupPx;
   const unsigned long long gt = (unsigned long long)part * kHsvThreads + tid;
   const unsigned long long T = (unsigned long long)nparts * kHsvThreads;
@@ -109,16 +159,16 @@ hist_hsv16_kernel(Addr addr, unsigned long long npx, int32_t* __restrict__ out, 
     for (i += T; i < ngroups; i += T) {
       unsigned nxt[12];
       hsv_load_group(f + i * (3 * kHsvGroupPx), aligned, nxt);
-      hsv_count_group<SWAP>(my, sdiv, hdiv, cur);
+      hsv_count_group<SWAP>(m, cur);
 #pragma unroll
       for (int k = 0; k < 12; ++k) cur[k] = nxt[k];
     }
-    hsv_count_group<SWAP>(my, sdiv, hdiv, cur);
+    hsv_count_group<SWAP>(m, cur);
   }
   // ragged end: fewer than 16 pixels
   if (part == 0) {
     const unsigned long long p = ngroups * kHsvGroupPx + tid;
-    if (p < npx) hsv_count_px<SWAP>(my, sdiv, hdiv, f[3 * p], f[3 * p + 1], f[3 * p + 2]);
+    if (p < npx) hsv_count_px<SWAP>(m, f[3 * p], f[3 * p + 1], f[3 * p + 2]);
   }
   __syncthreads();
 
