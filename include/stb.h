@@ -102,11 +102,12 @@ typedef struct stb_farneback_params {
   int num_levels;     /* 3   */
   double pyr_scale;   /* 0.5  (only 0.5 is implemented)            */
   int fast_pyramids;  /* 0    (only 0)                             */
-  int win_size;       /* 15   (odd, <= 31; box window)             */
+  int win_size;       /* 15   (odd, <= 31)                         */
   int num_iters;      /* 3                                         */
   int poly_n;         /* 5    (only 5)                             */
   double poly_sigma;  /* 1.2                                       */
-  int flags;          /* 0    (no Gaussian window, no initial flow) */
+  int flags;          /* 0 = box window (the reference); 256 = cv::OPTFLOW_FARNEBACK_GAUSSIAN
+                         (Gaussian window, generic kernel); OPTFLOW_USE_INITIAL_FLOW is not supported */
 } stb_farneback_params;
 
 typedef struct stb_farneback stb_farneback;

@@ -43,6 +43,14 @@ def optical_flow(frame0, frame1):
     return _finder.calc(gray(frame0), gray(frame1), None)
 
 
+def optical_flow_params(frame0, frame1, num_levels=3, win_size=15, num_iters=3, flags=0):
+    """The same op with other FarnebackOpticalFlow arguments (flags=256: OPTFLOW_FARNEBACK_GAUSSIAN);
+    the reference itself only ever uses FARNEBACK_ARGS."""
+    a = FARNEBACK_ARGS
+    return cv2.calcOpticalFlowFarneback(gray(frame0), gray(frame1), None, a['pyrScale'], num_levels, win_size,
+                                        num_iters, a['polyN'], a['polySigma'], flags)
+
+
 def flow_histogram(flow):
     """flow_histogram_kernel_cpu.cpp:27-54 -- int32[2][64]: magnitude [0,64), angle [0,360)."""
     x, y = cv2.split(flow)

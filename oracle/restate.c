@@ -379,6 +379,49 @@ static void update_flow_blur(const float* R0, const float* R1, float* flow, floa
   if (update) update_matrices(R0, R1, flow, M, w, h);
 }
 
+/* FarnebackUpdateFlow_GaussianBlur (flags & OPTFLOW_FARNEBACK_GAUSSIAN): separable Gaussian window
+ * sigma = 0.3 * (block/2), float taps normalised in double, float accumulation in OpenCV's order
+ * (centre first, then symmetric pairs), replicate border; same 2x2 solve in double. */
+static void update_flow_gaussian(const float* R0, const float* R1, float* flow, float* M, int w, int h,
+                                 int block, int update) {
+  int m = block / 2;
+  double sigma = m * 0.3, s = 1;
+  float kernel[64];
+  kernel[0] = (float)s;
+  for (int i = 1; i <= m; ++i) {
+    float t = (float)exp(-i * i / (2 * sigma * sigma));
+    kernel[i] = t;
+    s += t * 2;
+  }
+  s = 1. / s;
+  for (int i = 0; i <= m; ++i) kernel[i] = (float)(kernel[i] * s);
+  float* vs = (float*)malloc(sizeof(float) * (size_t)w * 5);
+  for (int y = 0; y < h; ++y) {
+    const float* rc = M + (size_t)y * w * 5;
+    for (int i = 0; i < w * 5; ++i) vs[i] = rc[i] * kernel[0];
+    for (int d = 1; d <= m; ++d) {
+      int ya = y + d > h - 1 ? h - 1 : y + d, yb = y - d < 0 ? 0 : y - d;
+      const float* ra = M + (size_t)ya * w * 5;
+      const float* rb = M + (size_t)yb * w * 5;
+      for (int i = 0; i < w * 5; ++i) vs[i] += (ra[i] + rb[i]) * kernel[d];
+    }
+    for (int x = 0; x < w; ++x) {
+      float hs[5];
+      for (int c = 0; c < 5; ++c) hs[c] = vs[x * 5 + c] * kernel[0];
+      for (int d = 1; d <= m; ++d) {
+        int xa = x - d < 0 ? 0 : x - d, xb = x + d > w - 1 ? w - 1 : x + d;
+        for (int c = 0; c < 5; ++c) hs[c] += kernel[d] * (vs[xa * 5 + c] + vs[xb * 5 + c]);
+      }
+      double g11 = hs[0], g12 = hs[1], g22 = hs[2], h1 = hs[3], h2 = hs[4];
+      double idet = 1. / (g11 * g22 - g12 * g12 + 1e-3);
+      flow[((size_t)y * w + x) * 2] = (float)((g11 * h2 - g12 * h1) * idet);
+      flow[((size_t)y * w + x) * 2 + 1] = (float)((g22 * h1 - g12 * h2) * idet);
+    }
+  }
+  free(vs);
+  if (update) update_matrices(R0, R1, flow, M, w, h);
+}
+
 typedef struct {
   int levels;       /* number of scales actually processed (<= 4 for numLevels = 3) */
   int w[8], h[8];   /* per scale k */
@@ -416,9 +459,11 @@ typedef struct {
   float* I0; float* I1; float* R0; float* R1; float* M0; float* flow_out;
 } orc_dump;
 
-ORC_API void orc_farneback_ex(const uint8_t* gray0, const uint8_t* gray1, int W, int H, float* flow_out,
-                              int num_levels, double pyr_scale, int winsize, int iters, int poly_n,
-                              double poly_sigma, orc_dump* dump) {
+#define ORC_FARNEBACK_GAUSSIAN 256 /* cv::OPTFLOW_FARNEBACK_GAUSSIAN */
+
+ORC_API void orc_farneback_flags(const uint8_t* gray0, const uint8_t* gray1, int W, int H, float* flow_out,
+                                 int num_levels, double pyr_scale, int winsize, int iters, int poly_n,
+                                 double poly_sigma, int flags, orc_dump* dump) {
   orc_pyr_info info;
   int levels = pyramid_levels(W, H, num_levels, pyr_scale, &info);
   poly_consts pc;
@@ -460,7 +505,10 @@ ORC_API void orc_farneback_ex(const uint8_t* gray0, const uint8_t* gray1, int W,
     float* M = (float*)malloc(sizeof(float) * n * 5);
     update_matrices(R[0], R[1], flow, M, w, h);
     if (dump && dump->level == k && dump->M0) memcpy(dump->M0, M, sizeof(float) * n * 5);
-    for (int i = 0; i < iters; ++i) update_flow_blur(R[0], R[1], flow, M, w, h, winsize, i < iters - 1);
+    for (int i = 0; i < iters; ++i) {
+      if (flags & ORC_FARNEBACK_GAUSSIAN) update_flow_gaussian(R[0], R[1], flow, M, w, h, winsize, i < iters - 1);
+      else update_flow_blur(R[0], R[1], flow, M, w, h, winsize, i < iters - 1);
+    }
     if (dump && dump->level == k && dump->flow_out) memcpy(dump->flow_out, flow, sizeof(float) * n * 2);
     free(M); free(R[0]); free(R[1]); free(I);
     free(prev_flow);
@@ -468,6 +516,12 @@ ORC_API void orc_farneback_ex(const uint8_t* gray0, const uint8_t* gray1, int W,
   }
   memcpy(flow_out, prev_flow, sizeof(float) * N * 2);
   free(prev_flow); free(fimg); free(blur);
+}
+
+ORC_API void orc_farneback_ex(const uint8_t* gray0, const uint8_t* gray1, int W, int H, float* flow_out,
+                              int num_levels, double pyr_scale, int winsize, int iters, int poly_n,
+                              double poly_sigma, orc_dump* dump) {
+  orc_farneback_flags(gray0, gray1, W, H, flow_out, num_levels, pyr_scale, winsize, iters, poly_n, poly_sigma, 0, dump);
 }
 
 /* the reference's fixed parameters: optical_flow_kernel_cpu.cpp:16 */

@@ -677,10 +677,17 @@ updmat_init_kernel(const float* __restrict__ R, const float* __restrict__ flow_c
 constexpr int kItTW = 64, kItTH = 32, kItThreads = 256;
 constexpr int kItMaxHalo = 15;  // win_size <= 31
 
-template <bool UPDATE>
+// GAUSS (flags & OPTFLOW_FARNEBACK_GAUSSIAN, OpenCV's FarnebackUpdateFlow_GaussianBlur): the box
+// sums become a separable Gaussian window, taps k[0..m] normalised to sum 1 per axis, accumulated
+// centre first, then symmetric pairs (OpenCV's order); no division by the window area.
+struct WinTaps {
+  float k[kItMaxHalo + 1];
+};
+
+template <bool UPDATE, bool GAUSS>
 __global__ void __launch_bounds__(kItThreads, 2)
 iter_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const float* __restrict__ R,
-            PtrBatch<float> flow_out, int w, int h, int m, int pair0) {
+            PtrBatch<float> flow_out, int w, int h, int m, int pair0, WinTaps taps) {
   STB_DYN_SMEM(float, sm);
   const int rawW = kItTW + 2 * m, rawH = kItTH + 2 * m;
   const int rawS = rawW + 2;              // row stride of raw
@@ -711,8 +718,14 @@ iter_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const float
       const int g = item / rawW, cx = item - g * rawW;
       const float* col = raw + (g * 8) * rawS + cx;
       for (int i = 0; i < 8; ++i) {      // direct sums: no add/subtract recurrence (see box15)
-        float s = 0.f;
-        for (int j = 0; j < win; ++j) s += col[(i + j) * rawS];
+        float s;
+        if (GAUSS) {
+          s = col[(i + m) * rawS] * taps.k[0];
+          for (int d = 1; d <= m; ++d) s += (col[(i + m + d) * rawS] + col[(i + m - d) * rawS]) * taps.k[d];
+        } else {
+          s = 0.f;
+          for (int j = 0; j < win; ++j) s += col[(i + j) * rawS];
+        }
         Vt[cx * 33 + g * 8 + i] = s;
       }
     }
@@ -722,8 +735,14 @@ iter_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const float
       const float* rowp = Vt + (warp * 8) * 33 + lane;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        float s = 0.f;
-        for (int j = 0; j < win; ++j) s += rowp[(i + j) * 33];
+        float s;
+        if (GAUSS) {
+          s = rowp[(i + m) * 33] * taps.k[0];
+          for (int d = 1; d <= m; ++d) s += taps.k[d] * (rowp[(i + m - d) * 33] + rowp[(i + m + d) * 33]);
+        } else {
+          s = 0.f;
+          for (int j = 0; j < win; ++j) s += rowp[(i + j) * 33];
+        }
         sums[c][i] = s;
       }
     }
@@ -733,7 +752,7 @@ iter_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const float
   }
   __syncthreads();  // all reads of raw/Vt done before fl (aliased) is written
 
-  const float inv_area = 1.f / (float)(win * win);
+  const float inv_area = GAUSS ? 1.f : 1.f / (float)(win * win);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float g11 = sums[0][i] * inv_area, g12 = sums[1][i] * inv_area, g22 = sums[2][i] * inv_area;
@@ -1175,6 +1194,7 @@ struct stb_farneback {
   int nscales;
   int w[8], h[8];
   PolyConsts pc;
+  WinTaps taps;     // Gaussian window taps (flags & OPTFLOW_FARNEBACK_GAUSSIAN), zero otherwise
   PyrParams pyr[kMaxScales];
   MergedTaps merged[kMaxScales];
   int pow2[kMaxScales];
@@ -1275,10 +1295,12 @@ static bool poly_consts(int n, double sigma, PolyConsts* pc) {
   return true;
 }
 
+constexpr int kFlagGaussian = 256;   // cv::OPTFLOW_FARNEBACK_GAUSSIAN
+
 static int validate_params(const stb_farneback_params& p) {
   if (p.num_levels < 0 || p.num_levels > kMaxScales - 1 || p.pyr_scale != 0.5 || p.fast_pyramids != 0 ||
       p.win_size < 3 || (p.win_size & 1) == 0 || p.win_size > 2 * kItMaxHalo + 1 || p.num_iters < 1 ||
-      p.poly_n != kPolyN || p.flags != 0) {
+      p.poly_n != kPolyN || (p.flags & ~kFlagGaussian) != 0) {
     set_error("stb_farneback: unsupported parameters (levels=%d pyr_scale=%g fast=%d win=%d iters=%d poly_n=%d flags=%d)",
               p.num_levels, p.pyr_scale, p.fast_pyramids, p.win_size, p.num_iters, p.poly_n, p.flags);
     return STB_ERR_UNSUPPORTED;
@@ -1391,6 +1413,22 @@ int stb_farneback_create(int width, int height, int max_pairs, const stb_farneba
   h->W = width; h->H = height; h->max_pairs = max_pairs; h->prm = p; h->dbg_level = -1;
   h->device = current_device();
   h->nscales = plan_levels(width, height, p, h->w, h->h);
+  {
+    // FarnebackUpdateFlow_GaussianBlur's window: sigma = 0.3 * (winSize / 2), float taps exp(-i^2 /
+    // (2 sigma^2)) normalised by their double-precision sum over the full (2m + 1)-tap window
+    for (int i = 0; i <= kItMaxHalo; ++i) h->taps.k[i] = 0.f;
+    const int m = p.win_size / 2;
+    const double sigma = m * 0.3;
+    double sum = 1;
+    h->taps.k[0] = 1.f;
+    for (int i = 1; i <= m; ++i) {
+      const float t = (float)std::exp(-i * i / (2 * sigma * sigma));
+      h->taps.k[i] = t;
+      sum += t * 2;
+    }
+    sum = 1. / sum;
+    for (int i = 0; i <= m; ++i) h->taps.k[i] = (float)(h->taps.k[i] * sum);
+  }
   if (!poly_consts(p.poly_n, p.poly_sigma, &h->pc)) {
     delete h;
     set_error("stb_farneback_create: singular polynomial basis (poly_sigma=%g)", p.poly_sigma);
@@ -1462,9 +1500,13 @@ int stb_farneback_create(int width, int height, int max_pairs, const stb_farneba
     }
   }
 #ifndef STB_CPU_EMU
-  e = cudaFuncSetAttribute(iter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iter_smem_bytes(kItMaxHalo));
+  e = cudaFuncSetAttribute(iter_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iter_smem_bytes(kItMaxHalo));
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(iter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iter_smem_bytes(kItMaxHalo));
+    e = cudaFuncSetAttribute(iter_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iter_smem_bytes(kItMaxHalo));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(iter_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iter_smem_bytes(kItMaxHalo));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(iter_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iter_smem_bytes(kItMaxHalo));
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(pyr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   if (e != cudaSuccess) {
@@ -1605,7 +1647,8 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
       for (int i = 0; i < np; ++i)
         fo.p[i] = (k == 0) ? d_flow[p0 + i] : h->flow[fl_cur] + (size_t)(p0 + i) * nk * 2;
       int mc = 0;
-      const bool fast15 = (m == kFiM);
+      const bool gauss = (h->prm.flags & kFlagGaussian) != 0;
+      const bool fast15 = (m == kFiM) && !gauss;   // the winSize-15 kernels are box-window only
       const dim3 grid = fast15 ? dim3(ceil_div(w, kFiTW), ceil_div(hh, kFiTH), np)
                                : dim3(ceil_div(w, kItTW), ceil_div(hh, kItTH), np);
       const bool prof = h->profile && k == 0 && h->prm.num_iters > 1;
@@ -1618,9 +1661,12 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
           else if (fast15)
             stb_launch(iter15_kernel<true, false>, grid, dim3(kFiThreads), 0, s, (const float*)h->M[mc], h->M[mc ^ 1],
                        (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0);
+          else if (gauss)
+            stb_launch(iter_kernel<true, true>, grid, dim3(kItThreads), it_smem, s, (const float*)h->M[mc], h->M[mc ^ 1],
+                       (const float*)h->R, fo, w, hh, m, p0, h->taps);
           else
-            stb_launch(iter_kernel<true>, grid, dim3(kItThreads), it_smem, s, (const float*)h->M[mc], h->M[mc ^ 1],
-                       (const float*)h->R, fo, w, hh, m, p0);
+            stb_launch(iter_kernel<true, false>, grid, dim3(kItThreads), it_smem, s, (const float*)h->M[mc], h->M[mc ^ 1],
+                       (const float*)h->R, fo, w, hh, m, p0, h->taps);
           mc ^= 1;
           if (prof && it == h->prm.num_iters - 2) {
             int prc = prof_mark(h, s);
@@ -1641,9 +1687,12 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
           else if (fast15)
             stb_launch(iter15_kernel<false, false>, grid, dim3(kFiThreads), 0, s, (const float*)h->M[mc], (float*)nullptr,
                        (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0);
+          else if (gauss)
+            stb_launch(iter_kernel<false, true>, grid, dim3(kItThreads), it_smem, s, (const float*)h->M[mc], (float*)nullptr,
+                       (const float*)h->R, fo, w, hh, m, p0, h->taps);
           else
-            stb_launch(iter_kernel<false>, grid, dim3(kItThreads), it_smem, s, (const float*)h->M[mc], (float*)nullptr,
-                       (const float*)h->R, fo, w, hh, m, p0);
+            stb_launch(iter_kernel<false, false>, grid, dim3(kItThreads), it_smem, s, (const float*)h->M[mc], (float*)nullptr,
+                       (const float*)h->R, fo, w, hh, m, p0, h->taps);
         }
         STB_CHECK_LAUNCH("iter_kernel");
       }

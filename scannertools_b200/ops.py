@@ -246,14 +246,21 @@ class OpticalFlow:
     flow frames (H x W x 2 f32); flow i maps frame i -> frame i+1 (the CPU kernel's direction,
     optical_flow_kernel_cpu.cpp:41)."""
 
-    def __init__(self, width, height, max_batch=16, device=None):
+    OPTFLOW_FARNEBACK_GAUSSIAN = 256
+
+    def __init__(self, width, height, max_batch=16, device=None, num_levels=3, win_size=15, num_iters=3, flags=0):
+        """The keyword defaults are the reference's hard-coded FarnebackOpticalFlow arguments
+        (optical_flow_kernel_cpu.cpp:16).  Other pyramid depths, odd windows <= 31, iteration
+        counts and flags=OPTFLOW_FARNEBACK_GAUSSIAN run on the generic kernels; anything else
+        raises StbError (STB_ERR_UNSUPPORTED)."""
         torch = _torch()
         self._lib = _lib.load()
         self.width, self.height, self.max_batch = int(width), int(height), int(max_batch)
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self._h = C.c_void_p()
+        prm = _lib.FarnebackParams(int(num_levels), 0.5, 0, int(win_size), int(num_iters), 5, 1.2, int(flags))
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.stb_farneback_create(self.width, self.height, self.max_batch, None, C.byref(self._h)), self._lib)
+            _lib.check(self._lib.stb_farneback_create(self.width, self.height, self.max_batch, C.byref(prm), C.byref(self._h)), self._lib)
 
     def close(self):
         if getattr(self, '_h', None) is not None and self._h:

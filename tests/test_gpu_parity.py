@@ -306,6 +306,28 @@ def test_farneback_parity_sizes(torch, ops, h, w, seed):
     of.close()
 
 
+@pytest.mark.parametrize('levels,win,iters,flags', [(3, 15, 3, 256), (2, 9, 2, 256), (3, 21, 3, 0), (1, 15, 1, 0), (3, 7, 4, 0)])
+def test_farneback_other_parameters(torch, ops, levels, win, iters, flags):
+    """FarnebackOpticalFlow arguments other than the reference's (generic kernels): the Gaussian
+    window (OPTFLOW_FARNEBACK_GAUSSIAN), other windows / depths / iteration counts -- against cv2
+    with the same arguments (or the pinned restatement when cv2 is missing)."""
+    h, w = 270, 480
+    clip = synth.textured_clip(11, 3, h, w)
+    of = ops.OpticalFlow(w, h, max_batch=2, num_levels=levels, win_size=win, num_iters=iters, flags=flags)
+    out, fh = of.execute_with_histogram(dev(torch, clip))
+    out, fh = out.cpu().numpy(), fh.cpu().numpy()
+    for i in range(2):
+        if cvo:
+            ref = cvo.optical_flow_params(clip[i], clip[i + 1], num_levels=levels, win_size=win, num_iters=iters, flags=flags)
+        else:
+            ref = restate.farneback(restate.gray(clip[i]), restate.gray(clip[i + 1]), winsize=win, iters=iters, levels=levels, flags=flags)
+        check_flow(out[i], ref, (levels, win, iters, flags, i))
+        assert np.array_equal(fh[i], o_flow_hist(out[i])), i          # the (unfused here) histogram of the flow produced
+    of.close()
+    with pytest.raises(_lib.StbError):
+        ops.OpticalFlow(w, h, flags=4)                               # OPTFLOW_USE_INITIAL_FLOW
+
+
 def test_farneback_batch_chunking_and_separate_buffers(torch, ops):
     """9 pairs at 160x120: several level chunks, B+1 separate frame buffers, results must not
     depend on batching (each pair equals its single-pair run bit for bit)."""
