@@ -1584,11 +1584,15 @@ static int prof_mark(stb_farneback* h, cudaStream_t s) {
   return STB_OK;
 }
 
+static inline bool fused_hist_available(const stb_farneback* h) {
+  return h->prm.win_size / 2 == kFiM && (h->prm.flags & kFlagGaussian) == 0;
+}
+
 // d_hist != NULL: fused FlowHistogram (n*128 int32, pre-zeroed) when the winSize-15 kernel runs;
 // returns through *hist_fused whether it did.  d_flow entries may be NULL only in that case.
 static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_t s, int32_t* d_hist = nullptr,
                       bool* hist_fused = nullptr) {
-  if (hist_fused) *hist_fused = (d_hist != nullptr) && (h->prm.win_size / 2 == kFiM);
+  if (hist_fused) *hist_fused = (d_hist != nullptr) && fused_hist_available(h);
   const int F = n + 1;
   const int m = h->prm.win_size / 2;
   const size_t it_smem = iter_smem_bytes(m);
@@ -1779,7 +1783,7 @@ int stb_farneback_run_hist(stb_farneback* h, const uint8_t* const* d_rgb, int n,
   if (n == 0) return STB_OK;
   if (!d_flow_hist) { set_error("stb_farneback_run_hist: d_flow_hist is NULL"); return STB_ERR_INVALID; }
   cudaStream_t s = (cudaStream_t)stream;
-  const bool fused = (h->prm.win_size / 2 == kFiM);   // the winSize-15 kernel bins the flow it produces
+  const bool fused = fused_hist_available(h);   // the winSize-15 box kernel bins the flow it produces
   float* tmp[kMaxPtrBatch * 4];
   float** fl = (n <= kMaxPtrBatch * 4) ? tmp : nullptr;
   float** heap = nullptr;
