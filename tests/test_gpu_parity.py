@@ -324,6 +324,7 @@ def test_farneback_other_parameters(torch, ops, levels, win, iters, flags):
         check_flow(out[i], ref, (levels, win, iters, flags, i))
         assert np.array_equal(fh[i], o_flow_hist(out[i])), i          # the (unfused here) histogram of the flow produced
     of.close()
+    from scannertools_b200 import _lib
     with pytest.raises(_lib.StbError):
         ops.OpticalFlow(w, h, flags=4)                               # OPTFLOW_USE_INITIAL_FLOW
 
