@@ -100,7 +100,7 @@ STB_API int stb_frame_diff(const uint8_t* d_prev, const uint8_t* d_cur, uint8_t*
  * Direction follows the CPU kernel: flow i maps frame i -> frame i+1. */
 typedef struct stb_farneback_params {
   int num_levels;     /* 3   */
-  double pyr_scale;   /* 0.5  (only 0.5 is implemented)            */
+  double pyr_scale;   /* 0.5  (0.5 <= pyr_scale < 1)               */
   int fast_pyramids;  /* 0    (only 0)                             */
   int win_size;       /* 15   (odd, <= 31)                         */
   int num_iters;      /* 3                                         */

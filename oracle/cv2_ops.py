@@ -43,11 +43,11 @@ def optical_flow(frame0, frame1):
     return _finder.calc(gray(frame0), gray(frame1), None)
 
 
-def optical_flow_params(frame0, frame1, num_levels=3, win_size=15, num_iters=3, flags=0):
+def optical_flow_params(frame0, frame1, num_levels=3, win_size=15, num_iters=3, flags=0, pyr_scale=0.5):
     """The same op with other FarnebackOpticalFlow arguments (flags=256: OPTFLOW_FARNEBACK_GAUSSIAN);
     the reference itself only ever uses FARNEBACK_ARGS."""
     a = FARNEBACK_ARGS
-    return cv2.calcOpticalFlowFarneback(gray(frame0), gray(frame1), None, a['pyrScale'], num_levels, win_size,
+    return cv2.calcOpticalFlowFarneback(gray(frame0), gray(frame1), None, pyr_scale, num_levels, win_size,
                                         num_iters, a['polyN'], a['polySigma'], flags)
 
 

@@ -40,7 +40,7 @@ def test_no_device_calls_fail_loudly_not_silently(built_lib):
     ws = built_lib.stb_farneback_workspace_bytes(1920, 1080, 16, None)
     assert 1 << 30 < ws < 8 << 30
     assert built_lib.stb_farneback_workspace_bytes(0, 1080, 16, None) == 0
-    bad = _lib.FarnebackParams(3, 0.8, 0, 15, 3, 5, 1.2, 0)
+    bad = _lib.FarnebackParams(3, 0.3, 0, 15, 3, 5, 1.2, 0)          # pyr_scale < 0.5 is not implemented
     assert built_lib.stb_farneback_workspace_bytes(640, 480, 1, C.byref(bad)) == 0
     if built_lib.stb_device_count() == 0:
         h = C.c_void_p()
