@@ -115,6 +115,37 @@ def test_shot_detection_c1_end_to_end(torch, ops, golden):
     assert np.array_equal(S2, S_h[500:])
 
 
+def test_pipeline_runners(torch, ops):
+    """The shipped pipelines composed from the ops (scannertools/old/histograms.py, old/optical_flow.py,
+    shot_detection.py): host frames in, chunked, results independent of the chunking."""
+    from scannertools_b200 import pipelines
+    clip, cuts = synth.cut_clip(5, 200, 90, 160, n_cuts=3)          # host numpy frames
+    ref = np.stack([o_hist(f) for f in clip])
+    assert np.array_equal(pipelines.compute_histograms(clip, batch=37), ref)
+    assert np.array_equal(pipelines.compute_histograms(dev(torch, clip), batch=64), ref)
+    hsv_ref = np.stack([o_hist(cvo.convert_color(f, 'COLOR_RGB2HSV') if cvo else restate.rgb2hsv(f)) for f in clip[:20]])
+    assert np.array_equal(pipelines.compute_hsv_histograms(clip[:20], batch=7), hsv_ref)
+    assert pipelines.detect_shots(clip, batch=33) == cuts == pipelines.detect_shots(dev(torch, clip), batch=200)
+    # Resize(426x240) -> OpticalFlow -> FlowHistogram (old/histograms.py:63-79) on 7 frames of 540p
+    mov = synth.textured_clip(3, 7, 540, 960)
+    fh = pipelines.compute_flow_histograms(mov, batch=4)
+    assert fh.shape == (6, 2, 64) and fh.dtype == np.int32
+    small = ops.resize(dev(torch, mov), width=426, height=240)
+    for i in range(7):
+        assert np.array_equal(small[i].cpu().numpy(), (cvo or restate).resize(mov[i], 426, 240))
+    of = ops.OpticalFlow(426, 240, max_batch=6)
+    flow = of.execute(small)
+    of.close()
+    assert np.array_equal(fh, ops.flow_histogram(flow).cpu().numpy())      # chunked + fused == one batch + stand-alone op
+    for i in (0, 5):
+        ref_flow = o_flow(small[i].cpu().numpy(), small[i + 1].cpu().numpy())
+        check_flow(flow[i].cpu().numpy(), ref_flow, ('pipeline', i))
+    got = [(a, f.clone()) for a, f in pipelines.compute_flow(small, batch=4)]
+    assert [a for a, _ in got] == [0, 4] and [f.shape[0] for _, f in got] == [4, 2]
+    assert torch.equal(torch.cat([f for _, f in got]), flow)
+    assert pipelines.compute_flow_histograms(mov[:1]).shape == (0, 2, 64) and pipelines.detect_shots(clip[:0]) == []
+
+
 def test_host_pipe_histogram(torch, ops):
     clip, cuts = synth.cut_clip(9, 70, 90, 160, n_cuts=3)
     pipe = ops.Pipe(160, 90, max_batch=16)
