@@ -203,6 +203,10 @@ def run_ours(args):
         raise SystemExit('bench.py: no CUDA device; scannertools_b200 has no CPU fallback '
                          '(use --impl reference for the CPU arm)')
     torch.cuda.set_device(local)
+    # feeder threads and pinned staging buffers on the GPU's own socket (no-op when the box
+    # does not expose the topology); STB_NO_NUMA_BIND=1 switches it off for A/B runs
+    from scannertools_b200 import sharding
+    numa_node = None if os.environ.get('STB_NO_NUMA_BIND') else sharding.bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     lib = _lib.load()
@@ -313,7 +317,7 @@ def run_ours(args):
             'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * t_dev / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': workload_config(args),
+            'config': dict(workload_config(args), host_numa_node_rank0=numa_node),
             'hbm_roofline_frac_whole_op': (FLOW1080_BYTES + FLOWHIST1080_BYTES) * value / world / (peak * 1e9),
             'roofline': {'bound': 'hbm', 'kernel': 'iter15_tma_kernel<true,false> (level-0 fused box-sum / 2x2 solve / update-matrices iteration, TMA-staged M tiles)',
                          'achieved': achieved, 'peak': peak, 'peak_kind': peak_kind, 'unit': 'GB/s',

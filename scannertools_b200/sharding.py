@@ -53,3 +53,41 @@ def sharded_shot_detection(frames_of_rank, n_frames, rank, world, histogram_fn, 
     scores = scores_fn(hist, prev_hist)
     all_scores = gather_frame_outputs(scores, n_frames, rank, world)
     return shot_detection.boundaries_from_scores(all_scores), all_scores
+
+
+def parse_cpulist(text):
+    """'0-3,8,10-11' (the sysfs cpulist format) -> [0, 1, 2, 3, 8, 10, 11]."""
+    cpus = []
+    for part in text.strip().split(','):
+        if not part:
+            continue
+        lo, _, hi = part.partition('-')
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index, sysfs='/sys'):
+    """Pins the calling process to the CPUs of the NUMA node the GPU hangs off, BEFORE it
+    allocates its pinned staging buffers, so those pages and the feeder threads sit on the
+    socket whose PCIe root complex serves that GPU (the >= 7x target at 8 GPUs 'is
+    threatened only by host-side feed: pinned-memory bandwidth, PCIe root-complex sharing, NUMA
+    placement of the feeder threads').  Returns the node number, or None when the topology is
+    not exposed (virtualised boxes report -1) -- in which case nothing is changed."""
+    import os
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bus = '%04x:%02x:%02x.0' % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open(os.path.join(sysfs, 'bus/pci/devices', bus, 'numa_node')) as f:
+            node = int(f.read())
+        if node < 0:
+            return None
+        with open(os.path.join(sysfs, 'devices/system/node/node%d/cpulist' % node)) as f:
+            cpus = parse_cpulist(f.read())
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError, RuntimeError, AssertionError):
+        return None

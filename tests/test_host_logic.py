@@ -54,3 +54,14 @@ def test_frame_ranges_cover_and_halo():
                 if p1 > p0:
                     assert (f0, f1) == (p0, p1 + 1)   # one halo frame
     assert sharding.stream_assignment(64, 8)[3] == [3, 11, 19, 27, 35, 43, 51, 59]
+
+
+def test_numa_binding_helpers(tmp_path):
+    from scannertools_b200 import sharding
+    assert sharding.parse_cpulist('0-3,8,10-11\n') == [0, 1, 2, 3, 8, 10, 11]
+    assert sharding.parse_cpulist('') == []
+    # no CUDA device / no topology: nothing changes and None comes back
+    import os
+    before = os.sched_getaffinity(0)
+    assert sharding.bind_to_gpu_numa_node(0, sysfs=str(tmp_path)) is None
+    assert os.sched_getaffinity(0) == before
