@@ -87,11 +87,7 @@ hist_rgb16_kernel(Addr addr, unsigned long long nbytes, int32_t* __restrict__ ou
   // 1-D grid over (frame, part): the first `rem` frames get base_blocks + 1 blocks, the others
   // base_blocks, so a batch fills the resident wave exactly whatever the frame count
   unsigned frame, part, nparts;
-  {
-    const unsigned b = blockIdx.x, big = rem * (base_blocks + 1u);
-    if (b < big) { frame = b / (base_blocks + 1u); part = b - frame * (base_blocks + 1u); nparts = base_blocks + 1u; }
-    else { const unsigned bb = b - big; frame = rem + bb / base_blocks; part = bb - (bb / base_blocks) * base_blocks; nparts = base_blocks; }
-  }
+  flat_grid_decode(blockIdx.x, base_blocks, rem, frame, part, nparts);
   STB_DYN_SMEM(unsigned char, dyn);
   const hist_addr_t origin = hist_origin(dyn);
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -223,11 +219,7 @@ __global__ void __launch_bounds__(kFlowHistThreads, 3)
 flow_hist_kernel(Addr addr, unsigned long long npx, int32_t* __restrict__ out, unsigned base_blocks, unsigned rem) {
   // 1-D grid over (frame, part), as in hist_rgb16_kernel
   unsigned frame, part, nparts;
-  {
-    const unsigned b = blockIdx.x, big = rem * (base_blocks + 1u);
-    if (b < big) { frame = b / (base_blocks + 1u); part = b - frame * (base_blocks + 1u); nparts = base_blocks + 1u; }
-    else { const unsigned bb = b - big; frame = rem + bb / base_blocks; part = bb - (bb / base_blocks) * base_blocks; nparts = base_blocks; }
-  }
+  flat_grid_decode(blockIdx.x, base_blocks, rem, frame, part, nparts);
   STB_DYN_SMEM(unsigned, sh);
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   {

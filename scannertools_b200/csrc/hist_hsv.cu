@@ -128,11 +128,7 @@ __global__ void __launch_bounds__(kHsvThreads, 3)
 hist_hsv16_kernel(Addr addr, unsigned long long npx, int32_t* __restrict__ out, unsigned base_blocks, unsigned rem) {
   // 1-D grid over (frame, part), as in hist_rgb16_kernel
   unsigned frame, part, nparts;
-  {
-    const unsigned b = blockIdx.x, big = rem * (base_blocks + 1u);
-    if (b < big) { frame = b / (base_blocks + 1u); part = b - frame * (base_blocks + 1u); nparts = base_blocks + 1u; }
-    else { const unsigned bb = b - big; frame = rem + bb / base_blocks; part = bb - (bb / base_blocks) * base_blocks; nparts = base_blocks; }
-  }
+  flat_grid_decode(blockIdx.x, base_blocks, rem, frame, part, nparts);
   STB_DYN_SMEM(unsigned, sh);
   int* sdiv = reinterpret_cast<int*>(sh + kHsvTableWords);
   int* hdiv = sdiv + 256;

@@ -54,6 +54,26 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// The per-frame streaming kernels (histograms) run on a flattened 1-D grid of exactly one
+// resident wave: `total` blocks are split over n frames as evenly as possible -- the first
+// rem = total % n frames get base_blocks + 1 blocks, the others base_blocks = total / n -- so a
+// batch fills every block slot whatever the frame count.  This maps a block index to
+// (frame, part of that frame, number of parts of that frame).
+__host__ __device__ inline void flat_grid_decode(unsigned b, unsigned base_blocks, unsigned rem, unsigned& frame,
+                                                 unsigned& part, unsigned& nparts) {
+  const unsigned big = rem * (base_blocks + 1u);
+  if (b < big) {
+    frame = b / (base_blocks + 1u);
+    part = b - frame * (base_blocks + 1u);
+    nparts = base_blocks + 1u;
+  } else {
+    const unsigned bb = b - big;
+    frame = rem + bb / base_blocks;
+    part = bb - (bb / base_blocks) * base_blocks;
+    nparts = base_blocks;
+  }
+}
 int num_sms();
 int current_device();
 int flow_hist_device(const float* const* d_flow, int n, unsigned long long npx, int32_t* d_out, cudaStream_t s,
