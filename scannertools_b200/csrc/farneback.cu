@@ -1083,10 +1083,23 @@ __device__ __forceinline__ void tma_load_tile(float* dst, const TmaMap3D* map, i
 }
 #endif
 
+// L2 prefetch of one box of a tensor map (no shared-memory destination, no completion to wait for)
+constexpr int kPfBoxW = 64, kPfBoxH = 40;   // R tile of the update phase + room for a few pixels of flow
+#ifdef STB_CPU_EMU
+__device__ __forceinline__ void tma_prefetch_l2(const TmaMap3D*, int, int, int) {}
+#else
+__device__ __forceinline__ void tma_prefetch_l2(const TmaMap3D* map, int x0, int y0, int z) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<unsigned long long>(map)),
+               "r"(x0), "r"(y0), "r"(z)
+               : "memory");
+}
+#endif
+
 template <bool UPDATE, bool HIST>
 __global__ void __launch_bounds__(kFiThreads, 4)
 iter15_tma_kernel(const STB_GRID_CONSTANT TmaMap3D map_in, float* __restrict__ Mout, const float* __restrict__ R,
-                  PtrBatch<float> flow_out, int32_t* __restrict__ flow_hist, int w, int h, int pair0) {
+                  PtrBatch<float> flow_out, int32_t* __restrict__ flow_hist, int w, int h, int pair0,
+                  const STB_GRID_CONSTANT TmaMap3D map_R, int prefetch_R) {
   __shared__ __align__(128) float raw[2][kTmStageFloats];     // also reused for the staged flow after the box phase
   __shared__ float Vt[2][kFiVtWords];
   __shared__ __align__(8) unsigned long long bars[2];
@@ -1116,6 +1129,13 @@ iter15_tma_kernel(const STB_GRID_CONSTANT TmaMap3D map_in, float* __restrict__ M
   if (tid == 0) {
     tma_load_tile(raw[0], &map_in, bx0, by0, pair * 5 + 0, &bars[0]);
     tma_load_tile(raw[1], &map_in, bx0, by0, pair * 5 + 1, &bars[1]);
+  }
+  if (UPDATE && prefetch_R && tid >= 32 && tid < 42) {
+    // the update phase at the end of this block reads this tile of R0 (frame `pair`) and, displaced
+    // by the flow, of R1 (frame pair + 1): pull both towards L2 while the box phase runs, so those
+    // loads find L2 hits instead of paying DRAM latency on the critical path
+    const int q = tid - 32;                      // 0..4: R0 planes, 5..9: R1 planes
+    tma_prefetch_l2(&map_R, ox0 - 8, oy0 - 4, pair * 5 + q);
   }
 
   // vertical item of this thread
@@ -1213,6 +1233,9 @@ struct stb_farneback {
   // TMA descriptors of the two M ping-pong buffers at every level ([5*P planes][h_k][w_k] floats)
   TmaMap3D tmap[2][kMaxScales];
   int use_tma[kMaxScales];
+  // R at every level ([5*F planes][h_k][w_k]) for the L2 prefetch of the update phase's tiles
+  TmaMap3D tmapR[kMaxScales];
+  int prefetch_R[kMaxScales];
   // measurement hook: event pairs around the level-0 update-iteration kernels
   int profile;
   std::vector<cudaEvent_t> ev_free;
@@ -1326,7 +1349,7 @@ static int plan_levels(int W, int H, const stb_farneback_params& p, int* ws, int
 }
 
 #ifdef STB_CPU_EMU
-static bool make_tmap(TmaMap3D* m, float* base, int w, int h, int planes) {
+static bool make_tmap(TmaMap3D* m, float* base, int w, int h, int planes, int = 0, int = 0) {
   m->base = base; m->w = w; m->h = h; m->planes = planes;
   return true;
 }
@@ -1349,13 +1372,13 @@ static PFN_encodeTiled get_encode_tiled() {
   }
   return fn;
 }
-// [planes][h][w] f32, box = 64 x 46 x 1, zero fill outside the tensor
-static bool make_tmap(TmaMap3D* m, float* base, int w, int h, int planes) {
+// [planes][h][w] f32, box = box_w x box_h x 1 (default: the 64 x 46 raw tile of the box filter), zero fill outside the tensor
+static bool make_tmap(TmaMap3D* m, float* base, int w, int h, int planes, int box_w = kTmRawW, int box_h = kTmRawH) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc || (w & 3) != 0 || (reinterpret_cast<uintptr_t>(base) & 15u) != 0) return false;
   const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)planes};
   const cuuint64_t strides[2] = {(cuuint64_t)w * sizeof(float), (cuuint64_t)w * h * sizeof(float)};
-  const cuuint32_t box[3] = {(cuuint32_t)kTmRawW, (cuuint32_t)kTmRawH, 1u};
+  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -1497,6 +1520,9 @@ int stb_farneback_create(int width, int height, int max_pairs, const stb_farneba
       if (make_tmap(&h->tmap[0][k], h->M[0], h->w[k], h->h[k], 5 * max_pairs) &&
           make_tmap(&h->tmap[1][k], h->M[1], h->w[k], h->h[k], 5 * max_pairs))
         h->use_tma[k] = 1;
+      if (h->use_tma[k] && !getenv("STB_NO_R_PREFETCH") && h->h[k] >= kPfBoxH &&
+          make_tmap(&h->tmapR[k], h->R, h->w[k], h->h[k], 5 * (max_pairs + 1), kPfBoxW, kPfBoxH))
+        h->prefetch_R[k] = 1;
     }
   }
 #ifndef STB_CPU_EMU
@@ -1661,7 +1687,7 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
           if (prof && it == 0) { int prc = prof_mark(h, s); if (prc) return prc; }
           if (fast15 && h->use_tma[k])
             stb_launch(iter15_tma_kernel<true, false>, grid, dim3(kFiThreads), 0, s, h->tmap[mc][k], h->M[mc ^ 1],
-                       (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0);
+                       (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0, h->tmapR[k], h->prefetch_R[k]);
           else if (fast15)
             stb_launch(iter15_kernel<true, false>, grid, dim3(kFiThreads), 0, s, (const float*)h->M[mc], h->M[mc ^ 1],
                        (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0);
@@ -1681,10 +1707,10 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
         } else {
           if (fast15 && h->use_tma[k] && k == 0 && d_hist != nullptr)
             stb_launch(iter15_tma_kernel<false, true>, grid, dim3(kFiThreads), 0, s, h->tmap[mc][k], (float*)nullptr,
-                       (const float*)h->R, fo, d_hist, w, hh, p0);
+                       (const float*)h->R, fo, d_hist, w, hh, p0, h->tmapR[k], 0);
           else if (fast15 && h->use_tma[k])
             stb_launch(iter15_tma_kernel<false, false>, grid, dim3(kFiThreads), 0, s, h->tmap[mc][k], (float*)nullptr,
-                       (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0);
+                       (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0, h->tmapR[k], 0);
           else if (fast15 && k == 0 && d_hist != nullptr)
             stb_launch(iter15_kernel<false, true>, grid, dim3(kFiThreads), 0, s, (const float*)h->M[mc], (float*)nullptr,
                        (const float*)h->R, fo, d_hist, w, hh, p0);
