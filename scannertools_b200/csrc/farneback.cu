@@ -320,6 +320,34 @@ pyr0_kernel(const uint8_t* __restrict__ gray, float* __restrict__ I, int W, int 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Tensor-map type and the TMA L2 prefetch, shared by updmat_init_kernel and iter15_tma_kernel.
+// A prefetch has no shared-memory destination and nothing to wait for: it only pulls one box of
+// the tensor towards L2.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPfBoxW = 48, kPfBoxH = 32;   // iteration kernel: exactly its 48 x 32 tile (the flow-displaced part of R1 is
+                                            // covered by the neighbouring tiles' own prefetches; a padded 64 x 40 box measured 1 % slower)
+constexpr int kPfInitBoxH = 8;              // updmat_init_kernel: exactly one of its 64 x 8 tiles
+#ifdef STB_CPU_EMU
+struct TmaMap3D {            // emulator stand-in for a CUtensorMap over [planes][h][w] floats
+  const float* base;
+  int w, h, planes;
+};
+#define STB_GRID_CONSTANT
+__device__ __forceinline__ void tma_prefetch_l2(const TmaMap3D*, int, int, int) {}
+#else
+}  // namespace stb
+#include <cuda.h>
+namespace stb {
+typedef CUtensorMap TmaMap3D;
+#define STB_GRID_CONSTANT __grid_constant__
+__device__ __forceinline__ void tma_prefetch_l2(const TmaMap3D* map, int x0, int y0, int z) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<unsigned long long>(map)),
+               "r"(x0), "r"(y0), "r"(z)
+               : "memory");
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // polynomial expansion (Appendix A.3): separable 11-tap, replicate borders.  I (h x w) ->
 // R (5 planes of h x w).  Tile 64 x 32, 256 threads.
 // ---------------------------------------------------------------------------------------------
@@ -334,6 +362,8 @@ constexpr int kPeRows = 8 + 2 * kPolyN;       // 18 input rows per vertical item
 // per component, 11-tap sums in registers, float4 stores of the 5 output planes.
 __global__ void __launch_bounds__(kPeThreads, 4)
 polyexp_kernel(const float* __restrict__ I, float* __restrict__ R, int w, int h, PolyConsts c, int frame0) {
+  // (A prefetch-ahead of the I tile, as in updmat_init_kernel, measured neutral here: the reads are
+  // 1/6 of this kernel's traffic.)
   __shared__ __align__(16) float V[3][kPeTH][kPeStride];
   const int tid = threadIdx.x;
   const int frame = frame0 + blockIdx.z;
@@ -624,11 +654,21 @@ __device__ __forceinline__ float2 upsample_flow(const float2* __restrict__ fc, i
 // kernel measured 12 % slower here (495 vs 440 us per 16-pair level-0 launch).
 __global__ void __launch_bounds__(256)
 updmat_init_kernel(const float* __restrict__ R, const float* __restrict__ flow_coarse, float* __restrict__ M,
-                   int w, int h, int wc, int hc, double scale_x, double scale_y, float flow_mul, int pair0) {
+                   int w, int h, int wc, int hc, double scale_x, double scale_y, float flow_mul, int pair0,
+                   const STB_GRID_CONSTANT TmaMap3D map_R, int prefetch_rows) {
+  const int pair = pair0 + blockIdx.z;
+  if (prefetch_rows > 0 && threadIdx.x < 10) {
+    // Blocks are issued x-fastest, then y: the tile `prefetch_rows` block-rows further down is
+    // picked up about two resident waves from now.  Pull its R0 / R1 planes towards L2 so that
+    // block's loads hit L2 instead of waiting on DRAM (every line is prefetched by exactly one block).
+    int brow = (int)blockIdx.y + prefetch_rows, pz = pair;
+    if (brow >= (int)gridDim.y) { brow -= (int)gridDim.y; ++pz; }   // wraps into the next pair of this launch
+    if (brow < (int)gridDim.y && pz < pair0 + (int)gridDim.z)
+      tma_prefetch_l2(&map_R, (int)blockIdx.x * 64, brow * 8, pz * 5 + (int)threadIdx.x);
+  }
   const int x = (blockIdx.x * 32 + (threadIdx.x & 31)) * 2;
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= w || y >= h) return;
-  const int pair = pair0 + blockIdx.z;
   const int n = w * h;
   const bool two = x + 1 < w;
   float2 da = make_float2(0.f, 0.f), db = make_float2(0.f, 0.f);
@@ -1029,11 +1069,6 @@ constexpr int kTmStageFloats = kTmRawW * kTmRawH;         // 2944 floats = 11776
 constexpr unsigned kTmStageBytes = kTmStageFloats * sizeof(float);
 
 #ifdef STB_CPU_EMU
-struct TmaMap3D {            // emulator stand-in for a CUtensorMap over [planes][h][w] floats
-  const float* base;
-  int w, h, planes;
-};
-#define STB_GRID_CONSTANT
 __device__ __forceinline__ void tma_mbar_init(unsigned long long*, int) {}
 // the emulated copy is synchronous in thread 0: a block barrier stands in for the mbarrier wait
 __device__ __forceinline__ void tma_mbar_wait(unsigned long long*, unsigned) { __syncthreads(); }
@@ -1046,11 +1081,6 @@ __device__ __forceinline__ void tma_load_tile(float* dst, const TmaMap3D* m, int
     }
 }
 #else
-}  // namespace stb
-#include <cuda.h>
-namespace stb {
-typedef CUtensorMap TmaMap3D;
-#define STB_GRID_CONSTANT __grid_constant__
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tma_mbar_init(unsigned long long* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -1080,18 +1110,6 @@ __device__ __forceinline__ void tma_load_tile(float* dst, const TmaMap3D* map, i
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<unsigned long long>(map)), "r"(x0), "r"(y0), "r"(z), "r"(smem_u32(bar))
       : "memory");
-}
-#endif
-
-// L2 prefetch of one box of a tensor map (no shared-memory destination, no completion to wait for)
-constexpr int kPfBoxW = 64, kPfBoxH = 40;   // R tile of the update phase + room for a few pixels of flow
-#ifdef STB_CPU_EMU
-__device__ __forceinline__ void tma_prefetch_l2(const TmaMap3D*, int, int, int) {}
-#else
-__device__ __forceinline__ void tma_prefetch_l2(const TmaMap3D* map, int x0, int y0, int z) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<unsigned long long>(map)),
-               "r"(x0), "r"(y0), "r"(z)
-               : "memory");
 }
 #endif
 
@@ -1133,10 +1151,14 @@ iter15_tma_kernel(const STB_GRID_CONSTANT TmaMap3D map_in, float* __restrict__ M
   if (UPDATE && prefetch_R && tid >= 32 && tid < 42) {
     // the update phase at the end of this block reads this tile of R0 (frame `pair`) and, displaced
     // by the flow, of R1 (frame pair + 1): pull both towards L2 while the box phase runs, so those
-    // loads find L2 hits instead of paying DRAM latency on the critical path
+    // loads find L2 hits instead of paying DRAM latency on the critical path (543 -> 522 us per
+    // 16-pair level-0 launch)
     const int q = tid - 32;                      // 0..4: R0 planes, 5..9: R1 planes
-    tma_prefetch_l2(&map_R, ox0 - 8, oy0 - 4, pair * 5 + q);
+    tma_prefetch_l2(&map_R, ox0, oy0, pair * 5 + q);
   }
+  // (Prefetching the NEXT tiles' M boxes the same way was measured and rejected: the halo'd boxes
+  // overlap 1.9x, and the extra L2 requests cost more than the first-load latency they hide --
+  // 628 vs 542 us per 16-pair level-0 launch.)
 
   // vertical item of this thread
   const int vg = tid >> 6, vcx = tid & 63;                     // 64 slots per row group, 62 active (see iter15_kernel)
@@ -1236,6 +1258,8 @@ struct stb_farneback {
   // R at every level ([5*F planes][h_k][w_k]) for the L2 prefetch of the update phase's tiles
   TmaMap3D tmapR[kMaxScales];
   int prefetch_R[kMaxScales];
+  TmaMap3D tmapRi[kMaxScales];   // same tensor, 64 x 8 boxes: updmat_init_kernel's prefetch-ahead
+  int prefetch_Ri[kMaxScales];
   // measurement hook: event pairs around the level-0 update-iteration kernels
   int profile;
   std::vector<cudaEvent_t> ev_free;
@@ -1523,6 +1547,9 @@ int stb_farneback_create(int width, int height, int max_pairs, const stb_farneba
       if (h->use_tma[k] && !getenv("STB_NO_R_PREFETCH") && h->h[k] >= kPfBoxH &&
           make_tmap(&h->tmapR[k], h->R, h->w[k], h->h[k], 5 * (max_pairs + 1), kPfBoxW, kPfBoxH))
         h->prefetch_R[k] = 1;
+      if (!(no_tma && no_tma[0] == '1') && !getenv("STB_NO_INIT_PREFETCH") &&
+          make_tmap(&h->tmapRi[k], h->R, h->w[k], h->h[k], 5 * (max_pairs + 1), 64, kPfInitBoxH))
+        h->prefetch_Ri[k] = 1;
     }
   }
 #ifndef STB_CPU_EMU
@@ -1661,8 +1688,14 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
         frames_done = fb;
       }
       (void)F;
-      stb_launch(updmat_init_kernel, dim3(ceil_div(w, 64), ceil_div(hh, 8), np), dim3(256), 0, s, (const float*)h->R,
-                 coarse, h->M[0], w, hh, wc, hc, up_sx, up_sy, (float)(1. / h->prm.pyr_scale), p0);
+      {
+        // prefetch distance: two resident waves (4 blocks/SM) expressed in block rows
+        const int bx = ceil_div(w, 64);
+        int ahead = h->prefetch_Ri[k] ? ceil_div(2 * 4 * num_sms(), bx) : 0;
+        if (const char* env = getenv("STB_INIT_PREFETCH_WAVES")) ahead = h->prefetch_Ri[k] ? ceil_div(atoi(env) * 4 * num_sms(), bx) : 0;
+        stb_launch(updmat_init_kernel, dim3(bx, ceil_div(hh, 8), np), dim3(256), 0, s, (const float*)h->R,
+                   coarse, h->M[0], w, hh, wc, hc, up_sx, up_sy, (float)(1. / h->prm.pyr_scale), p0, h->tmapRi[k], ahead);
+      }
       STB_CHECK_LAUNCH("updmat_init_kernel");
       if (dbg && h->dbg_pair >= p0 && h->dbg_pair < p1) {
         const int dp = h->dbg_pair;
