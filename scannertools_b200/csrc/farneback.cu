@@ -1156,9 +1156,10 @@ iter15_tma_kernel(const STB_GRID_CONSTANT TmaMap3D map_in, float* __restrict__ M
     const int q = tid - 32;                      // 0..4: R0 planes, 5..9: R1 planes
     tma_prefetch_l2(&map_R, ox0, oy0, pair * 5 + q);
   }
-  // (Prefetching the NEXT tiles' M boxes the same way was measured and rejected: the halo'd boxes
-  // overlap 1.9x, and the extra L2 requests cost more than the first-load latency they hide --
-  // 628 vs 542 us per 16-pair level-0 launch.)
+  // (Prefetching the M boxes of a tile one or two waves ahead, the way updmat_init_kernel does for
+  // R, was measured and rejected: 599-628 us vs 533-542 us per 16-pair level-0 launch, with
+  // halo'd 64 x 46 boxes as well as exact 48 x 32 tiles -- the prefetched lines do not survive in
+  // L2 until they are used, so the traffic is paid twice.)
 
   // vertical item of this thread
   const int vg = tid >> 6, vcx = tid & 63;                     // 64 slots per row group, 62 active (see iter15_kernel)
