@@ -1,6 +1,6 @@
 """Profiling target for `ncu --profile-from-start off`: one warm pass, then inside the
 cudaProfilerStart/Stop window one 1080p Farneback pair (+ flow histogram), one 4K histogram
-batch and one 1080p flow histogram."""
+batch (RGB and fused HSV) and one 1080p flow histogram."""
 import os
 import sys
 
@@ -26,6 +26,7 @@ def main():
             of.execute_with_histogram(fr)
         if 'hist' in what:
             ops.shot_scores(ops.histogram(f4k))
+            ops.histogram(f4k, hsv='COLOR_RGB2HSV')
         if 'flowhist' in what:
             ops.flow_histogram(flow)
     for _ in range(2):
