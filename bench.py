@@ -344,9 +344,11 @@ def run_ours(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of iter15_tma_kernel<true,false> at level 0 from the
-# committed `ncu --set full` capture (profiles/r01_ncu_full_table.txt: grid (40,34,16), 1.980 GB read
-# + 646 MB written for the 16 pairs of one launch), per PAIR; scaled by the pairs a bench launch processes.
-NCU_TRAFFIC_BYTES_PER_PAIR = (1.980e9 + 646.0e6) / 16
+# committed `ncu --set full` capture (profiles/r01_ncu_full_table.txt: grid (40,34,16), 2.204 GB read
+# + 644 MB written for the 16 pairs of one launch, mean of its two launches; the reads include the
+# L2 prefetch's double fetches, algorithmic bytes are 2.654 GB), per PAIR; scaled by the pairs a bench
+# launch processes.
+NCU_TRAFFIC_BYTES_PER_PAIR = (2.204e9 + 644.4e6) / 16
 
 
 def extra_workloads(torch, ops, lib, args):

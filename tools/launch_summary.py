@@ -27,8 +27,11 @@ if __name__ == '__main__':
     rows = load(sys.argv[1])
     marker = sys.argv[2] if len(sys.argv) > 2 else 'gray_kernel'
     idx = [i for i, r in enumerate(rows) if r['Kernel Name'].startswith(marker)]
+    which = int(sys.argv[3]) if len(sys.argv) > 3 else -2      # which occurrence of the marker starts the batch
     if len(idx) >= 2:
-        print('# one batch: launches %d..%d' % (idx[-2], idx[-1]))
-        summarise(rows[idx[-2]:idx[-1]])
+        a = idx[which]
+        b = idx[which + 1] if which + 1 != 0 and which + 1 < len(idx) else (idx[-1] if which < 0 else len(rows))
+        print('# one batch: launches %d..%d' % (a, b))
+        summarise(rows[a:b])
     else:
         summarise(rows)
