@@ -97,10 +97,10 @@ def shot_boundaries(hists):
     return boundaries
 
 
-def resize(frame, width, height):
-    """Resize op with the default interpolation (scannertools_cpp/imgproc/resize_kernel.cpp:31-35,69-71):
-    cv::resize(img, out, Size(width, height), 0, 0, INTER_LINEAR)."""
-    return cv2.resize(frame, (width, height), interpolation=cv2.INTER_LINEAR)
+def resize(frame, width, height, interpolation='INTER_LINEAR'):
+    """Resize op (scannertools_cpp/imgproc/resize_kernel.cpp:31-35,69-71):
+    cv::resize(img, out, Size(width, height), 0, 0, <interpolation>), INTER_LINEAR by default."""
+    return cv2.resize(frame, (width, height), interpolation=getattr(cv2, interpolation))
 
 
 def convert_color(frame, conversion):

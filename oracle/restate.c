@@ -591,6 +591,121 @@ ORC_API void orc_resize_linear_u8(const uint8_t* src, int sw, int sh, int cn, ui
   free(xofs); free(xa);
 }
 
+/* ---- Resize with the other interpolation names the reference maps (resize_kernel.cpp:9-20):
+ * INTER_NEAREST and INTER_AREA on 8-bit frames, as OpenCV 4.x executes them (imgproc/src/resize.cpp).
+ *   NEAREST: sx = min(floor(dx * (1 / inv_scale_x)), sw - 1), same for y.
+ *   AREA, both scales >= 1: integer factors -> block sums, (a+b+c+d+2)>>2 for 2x2, otherwise
+ *         saturate(round(sum * (1.f / area))); else the general table of (index, float weight)
+ *         per axis (computeResizeAreaTab) with float accumulation in table order:
+ *         buf = sum_x S*alpha; sum = beta0*buf0, then sum += beta*buf.
+ *   AREA with an up-scaled axis: INTER_LINEAR arithmetic with the "area" coefficient
+ *         fx = (dx+1) - (sx+1)*inv_scale, sx = floor(dx*scale).
+ * Verified bit-exact against cv2 4.13 (tests/test_oracle.py). */
+enum { ORC_INTER_LINEAR = 0, ORC_INTER_NEAREST = 1, ORC_INTER_AREA = 2 };
+
+typedef struct { int di, si; float alpha; } area_tab_t;
+
+static int area_tab(int ssize, int dsize, double scale, area_tab_t* tab) {
+  int k = 0;
+  for (int dx = 0; dx < dsize; ++dx) {
+    double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+    double cell = scale < ssize - fsx1 ? scale : ssize - fsx1;
+    int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+    if (sx2 > ssize - 1) sx2 = ssize - 1;
+    if (sx1 > sx2) sx1 = sx2;
+    if (sx1 - fsx1 > 1e-3) { tab[k].di = dx; tab[k].si = sx1 - 1; tab[k++].alpha = (float)((sx1 - fsx1) / cell); }
+    for (int sx = sx1; sx < sx2; ++sx) { tab[k].di = dx; tab[k].si = sx; tab[k++].alpha = (float)(1.0 / cell); }
+    if (fsx2 - sx2 > 1e-3) {
+      double a = fsx2 - sx2; if (a > 1.) a = 1.; if (a > cell) a = cell;
+      tab[k].di = dx; tab[k].si = sx2; tab[k++].alpha = (float)(a / cell);
+    }
+  }
+  return k;
+}
+
+static uint8_t sat_u8_f(float v) { long r = lrintf(v); return (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r)); }
+
+static void resize_linear_area_mode(const uint8_t* src, int sw, int sh, int cn, uint8_t* dst, int dw, int dh) {
+  double inv_x = (double)dw / sw, inv_y = (double)dh / sh, scale_x = 1. / inv_x, scale_y = 1. / inv_y;
+  for (int dy = 0; dy < dh; ++dy) {
+    int sy = (int)floor(dy * scale_y);
+    float fy = (float)((dy + 1) - (sy + 1) * inv_y);
+    fy = fy <= 0 ? 0.f : fy - floorf(fy);
+    int b0 = cv_round((double)((1.f - fy) * 2048.f)), b1 = cv_round((double)(fy * 2048.f));
+    int y0 = sy < 0 ? 0 : (sy > sh - 1 ? sh - 1 : sy);
+    int y1 = sy + 1 < 0 ? 0 : (sy + 1 > sh - 1 ? sh - 1 : sy + 1);
+    const uint8_t* r0 = src + (size_t)y0 * sw * cn;
+    const uint8_t* r1 = src + (size_t)y1 * sw * cn;
+    for (int dx = 0; dx < dw; ++dx) {
+      int sx = (int)floor(dx * scale_x);
+      float fx = (float)((dx + 1) - (sx + 1) * inv_x);
+      fx = fx <= 0 ? 0.f : fx - floorf(fx);
+      if (sx < 0) { fx = 0; sx = 0; }
+      if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+      int sx1 = sx + 1 < sw ? sx + 1 : sx;
+      int a0 = cv_round((double)((1.f - fx) * 2048.f)), a1 = cv_round((double)(fx * 2048.f));
+      for (int c = 0; c < cn; ++c) {
+        int h0 = r0[sx * cn + c] * a0 + r0[sx1 * cn + c] * a1;
+        int h1 = r1[sx * cn + c] * a0 + r1[sx1 * cn + c] * a1;
+        int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        dst[((size_t)dy * dw + dx) * cn + c] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+      }
+    }
+  }
+}
+
+ORC_API int orc_resize_u8(const uint8_t* src, int sw, int sh, int cn, uint8_t* dst, int dw, int dh, int interp) {
+  if (interp == ORC_INTER_LINEAR) { orc_resize_linear_u8(src, sw, sh, cn, dst, dw, dh); return 0; }
+  double inv_x = (double)dw / sw, inv_y = (double)dh / sh, scale_x = 1. / inv_x, scale_y = 1. / inv_y;
+  if (interp == ORC_INTER_NEAREST) {
+    for (int y = 0; y < dh; ++y) {
+      int sy = (int)floor(y * scale_y); if (sy > sh - 1) sy = sh - 1;
+      for (int x = 0; x < dw; ++x) {
+        int sx = (int)floor(x * scale_x); if (sx > sw - 1) sx = sw - 1;
+        memcpy(dst + ((size_t)y * dw + x) * cn, src + ((size_t)sy * sw + sx) * cn, (size_t)cn);
+      }
+    }
+    return 0;
+  }
+  if (interp != ORC_INTER_AREA) return -1;
+  if (!(scale_x >= 1 && scale_y >= 1)) { resize_linear_area_mode(src, sw, sh, cn, dst, dw, dh); return 0; }
+  int isx = cv_round(scale_x), isy = cv_round(scale_y);
+  if (fabs(scale_x - isx) < 2.220446049250313e-16 && fabs(scale_y - isy) < 2.220446049250313e-16) {
+    float scale = 1.f / (isx * isy);
+    for (int y = 0; y < dh; ++y)
+      for (int x = 0; x < dw; ++x)
+        for (int c = 0; c < cn; ++c) {
+          int sum = 0;
+          for (int j = 0; j < isy; ++j)
+            for (int i = 0; i < isx; ++i) sum += src[((size_t)(y * isy + j) * sw + (x * isx + i)) * cn + c];
+          dst[((size_t)y * dw + x) * cn + c] = (isx == 2 && isy == 2) ? (uint8_t)((sum + 2) >> 2) : sat_u8_f(sum * scale);
+        }
+    return 0;
+  }
+  area_tab_t* xt = (area_tab_t*)malloc(sizeof(area_tab_t) * ((size_t)sw * 2 + dw * 2));
+  area_tab_t* yt = (area_tab_t*)malloc(sizeof(area_tab_t) * ((size_t)sh * 2 + dh * 2));
+  int nx = area_tab(sw, dw, scale_x, xt), ny = area_tab(sh, dh, scale_y, yt);
+  float* buf = (float*)malloc(sizeof(float) * (size_t)dw * cn);
+  float* sum = (float*)malloc(sizeof(float) * (size_t)dw * cn);
+  int prev = -1;
+  for (int j = 0; j < ny; ++j) {
+    const uint8_t* S = src + (size_t)yt[j].si * sw * cn;
+    for (int i = 0; i < dw * cn; ++i) buf[i] = 0.f;
+    for (int k = 0; k < nx; ++k)
+      for (int c = 0; c < cn; ++c) buf[xt[k].di * cn + c] = buf[xt[k].di * cn + c] + S[xt[k].si * cn + c] * xt[k].alpha;
+    if (yt[j].di != prev) {
+      if (prev >= 0) for (int i = 0; i < dw * cn; ++i) dst[(size_t)prev * dw * cn + i] = sat_u8_f(sum[i]);
+      for (int i = 0; i < dw * cn; ++i) sum[i] = yt[j].alpha * buf[i];
+      prev = yt[j].di;
+    } else {
+      for (int i = 0; i < dw * cn; ++i) sum[i] = sum[i] + yt[j].alpha * buf[i];
+    }
+  }
+  if (prev >= 0) for (int i = 0; i < dw * cn; ++i) dst[(size_t)prev * dw * cn + i] = sat_u8_f(sum[i]);
+  free(xt); free(yt); free(buf); free(sum);
+  return 0;
+}
+
 /* ---- ConvertColor (next row): cv::cvtColor RGB2HSV on 8-bit frames -------------
  * old/cpp_ops/imgproc.cpp:41.  OpenCV's integer path (hsv_shift = 12, H range 180). */
 ORC_API void orc_rgb2hsv_u8(const uint8_t* rgb, size_t n_px, uint8_t* hsv) {

@@ -123,12 +123,17 @@ def optical_flow(frame0, frame1):
     return out
 
 
-def resize(frame, width, height):
+RESIZE_INTERP = {'INTER_LINEAR': 0, 'INTER_NEAREST': 1, 'INTER_AREA': 2}
+
+
+def resize(frame, width, height, interpolation='INTER_LINEAR'):
     f = np.ascontiguousarray(frame, np.uint8)
     sh, sw = f.shape[:2]
     cn = f.shape[2] if f.ndim == 3 else 1
     out = np.empty((height, width) + ((cn,) if f.ndim == 3 else ()), np.uint8)
-    lib().orc_resize_linear_u8(_p(f), C.c_int(sw), C.c_int(sh), C.c_int(cn), _p(out), C.c_int(width), C.c_int(height))
+    rc = lib().orc_resize_u8(_p(f), C.c_int(sw), C.c_int(sh), C.c_int(cn), _p(out), C.c_int(width), C.c_int(height),
+                             C.c_int(RESIZE_INTERP[interpolation]))
+    assert rc == 0
     return out
 
 

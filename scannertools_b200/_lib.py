@@ -44,6 +44,8 @@ SIGNATURES = {
     'stb_farneback_debug_set': (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     'stb_resize_target': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'stb_resize_bilinear_u8': (C.c_int, [_u8pp, C.c_int, C.c_int, C.c_int, C.c_int, _u8pp, C.c_int, C.c_int, _vp]),
+    'stb_resize_interp_code': (C.c_int, [C.c_char_p]),
+    'stb_resize_u8': (C.c_int, [_u8pp, C.c_int, C.c_int, C.c_int, C.c_int, _u8pp, C.c_int, C.c_int, C.c_int, _vp]),
     'stb_color_code': (C.c_int, [C.c_char_p]),
     'stb_color_out_channels': (C.c_int, [C.c_int]),
     'stb_convert_color_u8': (C.c_int, [_u8pp, C.c_int, C.c_int, C.c_int, C.c_int, _u8pp, _vp]),

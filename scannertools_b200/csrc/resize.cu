@@ -8,6 +8,13 @@
 // index/fraction are clamped when the coefficient is formed, y keeps the unclamped fraction and
 // clips the two row indices -- exactly OpenCV's asymmetry (it changes results on up-scaled
 // border rows).  Exact 2x down-scaling takes OpenCV's INTER_AREA fast path (a+b+c+d+2)>>2.
+//
+// The other interpolation names the reference maps (resize_kernel.cpp:9-20) that are implemented:
+// INTER_NEAREST and INTER_AREA (integer-factor block averages, the general weighted-cell tables with
+// OpenCV's float accumulation order, and the linear "area" coefficients when an axis is up-scaled),
+// all bit-exact with cv2 4.13.  INTER_CUBIC / INTER_LANCZOS4 return STB_ERR_UNSUPPORTED.
+#include <cmath>
+
 #include "stb_rt.h"
 
 namespace stb {
@@ -17,12 +24,14 @@ struct PtrAddrPairU8 {
   PtrBatch<uint8_t> dst;
 };
 
+enum { kInterpLinear = 0, kInterpNearest = 1, kInterpArea = 2 };
+
 __device__ __forceinline__ int cv_round_f(float v) { return __float2int_rn(v); }
 
 template <int CN>
 __global__ void __launch_bounds__(256)
 resize_linear_u8_kernel(PtrBatch<const uint8_t> srcs, PtrBatch<uint8_t> dsts, int sw, int sh, int dw, int dh,
-                        double scale_x, double scale_y, int area2x) {
+                        double scale_x, double scale_y, int area2x, int area_mode) {
   const int dx = blockIdx.x * 32 + (threadIdx.x & 31);
   const int dy = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (dx >= dw || dy >= dh) return;
@@ -35,16 +44,30 @@ resize_linear_u8_kernel(PtrBatch<const uint8_t> srcs, PtrBatch<uint8_t> dsts, in
     for (int c = 0; c < CN; ++c) dst[c] = (uint8_t)((p[c] + p[CN + c] + p[rs + c] + p[rs + CN + c] + 2) >> 2);
     return;
   }
-  float fx = (float)((dx + 0.5) * scale_x - 0.5);
-  int sx = __float2int_rd(fx);
-  fx -= (float)sx;
+  float fx, fy;
+  int sx, sy;
+  if (!area_mode) {
+    fx = (float)((dx + 0.5) * scale_x - 0.5);
+    sx = __float2int_rd(fx);
+    fx -= (float)sx;
+    fy = (float)((dy + 0.5) * scale_y - 0.5);
+    sy = __float2int_rd(fy);
+    fy -= (float)sy;
+  } else {
+    // INTER_AREA with an up-scaled axis: linear arithmetic, "area" coefficients
+    // (inv_scale is the double dsize/ssize, scale = 1/inv_scale, as cv::resize forms them)
+    const double inv_x = (double)dw / sw, inv_y = (double)dh / sh;
+    sx = __double2int_rd(dx * scale_x);
+    fx = (float)((dx + 1) - (sx + 1) * inv_x);
+    fx = fx <= 0.f ? 0.f : fx - floorf(fx);
+    sy = __double2int_rd(dy * scale_y);
+    fy = (float)((dy + 1) - (sy + 1) * inv_y);
+    fy = fy <= 0.f ? 0.f : fy - floorf(fy);
+  }
   if (sx < 0) { fx = 0.f; sx = 0; }
   if (sx >= sw - 1) { fx = 0.f; sx = sw - 1; }
   const int sx1 = sx + 1 < sw ? sx + 1 : sx;
   const int a0 = cv_round_f(__fmul_rn(1.f - fx, 2048.f)), a1 = cv_round_f(__fmul_rn(fx, 2048.f));
-  float fy = (float)((dy + 0.5) * scale_y - 0.5);
-  const int sy = __float2int_rd(fy);
-  fy -= (float)sy;
   const int b0 = cv_round_f(__fmul_rn(1.f - fy, 2048.f)), b1 = cv_round_f(__fmul_rn(fy, 2048.f));
   const int y0 = min(max(sy, 0), sh - 1), y1 = min(max(sy + 1, 0), sh - 1);
   const uint8_t* r0 = src + (size_t)y0 * sw * CN;
@@ -56,6 +79,113 @@ resize_linear_u8_kernel(PtrBatch<const uint8_t> srcs, PtrBatch<uint8_t> dsts, in
     const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
     dst[c] = (uint8_t)min(max(v, 0), 255);
   }
+}
+
+// INTER_NEAREST: sx = min(floor(dx * scale_x), sw - 1) (cv::resizeNN)
+template <int CN>
+__global__ void __launch_bounds__(256)
+resize_nearest_u8_kernel(PtrBatch<const uint8_t> srcs, PtrBatch<uint8_t> dsts, int sw, int sh, int dw, int dh,
+                         double scale_x, double scale_y) {
+  const int dx = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int dy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (dx >= dw || dy >= dh) return;
+  const int sx = min(__double2int_rd(dx * scale_x), sw - 1), sy = min(__double2int_rd(dy * scale_y), sh - 1);
+  const uint8_t* p = srcs.p[blockIdx.z] + ((size_t)sy * sw + sx) * CN;
+  uint8_t* dst = dsts.p[blockIdx.z] + ((size_t)dy * dw + dx) * CN;
+#pragma unroll
+  for (int c = 0; c < CN; ++c) dst[c] = p[c];
+}
+
+// INTER_AREA, integer factors (cv::ResizeAreaFast): block sum, (s + 2) >> 2 for 2x2, otherwise
+// saturate(round(sum * (1.f / area)))
+template <int CN>
+__global__ void __launch_bounds__(256)
+resize_area_int_u8_kernel(PtrBatch<const uint8_t> srcs, PtrBatch<uint8_t> dsts, int sw, int dw, int dh, int isx, int isy) {
+  const int dx = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int dy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (dx >= dw || dy >= dh) return;
+  const uint8_t* p = srcs.p[blockIdx.z] + ((size_t)(dy * isy) * sw + (size_t)dx * isx) * CN;
+  uint8_t* dst = dsts.p[blockIdx.z] + ((size_t)dy * dw + dx) * CN;
+  int sum[CN];
+#pragma unroll
+  for (int c = 0; c < CN; ++c) sum[c] = 0;
+  for (int j = 0; j < isy; ++j) {
+    const uint8_t* r = p + (size_t)j * sw * CN;
+    for (int i = 0; i < isx; ++i) {
+#pragma unroll
+      for (int c = 0; c < CN; ++c) sum[c] += r[i * CN + c];
+    }
+  }
+  const float scale = __fdiv_rn(1.f, (float)(isx * isy));
+#pragma unroll
+  for (int c = 0; c < CN; ++c) {
+    const int v = (isx == 2 && isy == 2) ? (sum[c] + 2) >> 2 : __float2int_rn(__fmul_rn((float)sum[c], scale));
+    dst[c] = (uint8_t)min(max(v, 0), 255);
+  }
+}
+
+// One destination index of cv::computeResizeAreaTab: the source cells [first, first + n) it covers
+// and their float weights, in table order (optional partial first cell, full cells, optional
+// partial last cell).
+struct AreaSpan {
+  int first, n;
+  float a_first, a_mid, a_last;
+  bool has_first, has_last;
+  __device__ __forceinline__ float alpha(int k) const {
+    if (k == 0 && has_first) return a_first;
+    if (k == n - 1 && has_last) return a_last;
+    return a_mid;
+  }
+};
+
+__device__ __forceinline__ AreaSpan area_span(int d, double scale, int ssize) {
+  const double f1 = d * scale, f2 = f1 + scale;
+  const double cell = fmin(scale, ssize - f1);
+  int s1 = __double2int_ru(f1), s2 = __double2int_rd(f2);
+  s2 = min(s2, ssize - 1);
+  s1 = min(s1, s2);
+  AreaSpan sp;
+  sp.has_first = (s1 - f1) > 1e-3;
+  sp.has_last = (f2 - s2) > 1e-3;
+  sp.a_first = (float)((s1 - f1) / cell);
+  sp.a_mid = (float)(1.0 / cell);
+  sp.a_last = (float)(fmin(fmin(f2 - s2, 1.0), cell) / cell);
+  sp.first = sp.has_first ? s1 - 1 : s1;
+  sp.n = (s2 - s1) + (sp.has_first ? 1 : 0) + (sp.has_last ? 1 : 0);
+  return sp;
+}
+
+// INTER_AREA, general down-scaling (cv::ResizeArea_Invoker): float accumulation in table order,
+// no FMA contraction: buf = sum_x S * alpha (from 0), sum = beta_0 * buf_0, sum += beta_j * buf_j.
+template <int CN>
+__global__ void __launch_bounds__(256)
+resize_area_u8_kernel(PtrBatch<const uint8_t> srcs, PtrBatch<uint8_t> dsts, int sw, int sh, int dw, int dh,
+                      double scale_x, double scale_y) {
+  const int dx = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int dy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (dx >= dw || dy >= dh) return;
+  const AreaSpan xs = area_span(dx, scale_x, sw), ys = area_span(dy, scale_y, sh);
+  const uint8_t* src = srcs.p[blockIdx.z];
+  uint8_t* dst = dsts.p[blockIdx.z] + ((size_t)dy * dw + dx) * CN;
+  float sum[CN];
+#pragma unroll
+  for (int c = 0; c < CN; ++c) sum[c] = 0.f;
+  for (int j = 0; j < ys.n; ++j) {
+    const uint8_t* r = src + ((size_t)(ys.first + j) * sw + xs.first) * CN;
+    float buf[CN];
+#pragma unroll
+    for (int c = 0; c < CN; ++c) buf[c] = 0.f;
+    for (int i = 0; i < xs.n; ++i) {
+      const float a = xs.alpha(i);
+#pragma unroll
+      for (int c = 0; c < CN; ++c) buf[c] = __fadd_rn(buf[c], __fmul_rn((float)r[i * CN + c], a));
+    }
+    const float beta = ys.alpha(j);
+#pragma unroll
+    for (int c = 0; c < CN; ++c) sum[c] = j == 0 ? __fmul_rn(beta, buf[c]) : __fadd_rn(sum[c], __fmul_rn(beta, buf[c]));
+  }
+#pragma unroll
+  for (int c = 0; c < CN; ++c) dst[c] = (uint8_t)min(max(__float2int_rn(sum[c]), 0), 255);
 }
 
 }  // namespace stb
@@ -80,35 +210,68 @@ int stb_resize_target(int frame_w, int frame_h, int width, int height, int min_f
   return STB_OK;
 }
 
+int stb_resize_interp_code(const char* name) {
+  if (!name || !*name) return kInterpLinear;
+  const char* names[] = {"INTER_LINEAR", "INTER_NEAREST", "INTER_AREA"};
+  for (int i = 0; i < 3; ++i) {
+    const char* a = names[i];
+    const char* b = name;
+    while (*a && *a == *b) { ++a; ++b; }
+    if (*a == 0 && *b == 0) return i;
+  }
+  return -1;
+}
+
 int stb_resize_bilinear_u8(const uint8_t* const* d_src, int n, int src_w, int src_h, int channels, uint8_t* const* d_dst,
                            int dst_w, int dst_h, stb_stream_t stream) {
+  return stb_resize_u8(d_src, n, src_w, src_h, channels, d_dst, dst_w, dst_h, kInterpLinear, stream);
+}
+
+#define STB_RESIZE_DISPATCH(KERNEL, ...)                                                     \
+  do {                                                                                       \
+    if (channels == 3) stb_launch(KERNEL<3>, grid, dim3(256), 0, s, a, b, __VA_ARGS__);      \
+    else if (channels == 1) stb_launch(KERNEL<1>, grid, dim3(256), 0, s, a, b, __VA_ARGS__); \
+    else stb_launch(KERNEL<4>, grid, dim3(256), 0, s, a, b, __VA_ARGS__);                    \
+  } while (0)
+
+int stb_resize_u8(const uint8_t* const* d_src, int n, int src_w, int src_h, int channels, uint8_t* const* d_dst,
+                  int dst_w, int dst_h, int interp, stb_stream_t stream) {
   if (n == 0) return STB_OK;
   if (!d_src || !d_dst || n < 0 || src_w <= 0 || src_h <= 0 || dst_w <= 0 || dst_h <= 0) {
-    set_error("stb_resize_bilinear_u8: invalid argument (n=%d, %dx%d -> %dx%d)", n, src_w, src_h, dst_w, dst_h);
+    set_error("stb_resize_u8: invalid argument (n=%d, %dx%d -> %dx%d)", n, src_w, src_h, dst_w, dst_h);
     return STB_ERR_INVALID;
   }
   if (channels != 1 && channels != 3 && channels != 4) {
-    set_error("stb_resize_bilinear_u8: %d channels not supported (1, 3, 4)", channels);
+    set_error("stb_resize_u8: %d channels not supported (1, 3, 4)", channels);
+    return STB_ERR_UNSUPPORTED;
+  }
+  if (interp != kInterpLinear && interp != kInterpNearest && interp != kInterpArea) {
+    set_error("stb_resize_u8: interpolation %d is not implemented (INTER_LINEAR, INTER_NEAREST, INTER_AREA)", interp);
     return STB_ERR_UNSUPPORTED;
   }
   cudaStream_t s = (cudaStream_t)stream;
   const double scale_x = 1. / ((double)dst_w / src_w), scale_y = 1. / ((double)dst_h / src_h);
-  const int area2x = (src_w == 2 * dst_w && src_h == 2 * dst_h) ? 1 : 0;
+  // cv::resize: iscale = saturate_cast<int>(scale) (round half even); "fast area" when both are integers
+  const int isx = (int)std::nearbyint(scale_x), isy = (int)std::nearbyint(scale_y);
+  const bool int_scale = std::fabs(scale_x - isx) < 2.220446049250313e-16 && std::fabs(scale_y - isy) < 2.220446049250313e-16;
+  const bool down = scale_x >= 1 && scale_y >= 1;
+  const int area2x = (interp == kInterpLinear && src_w == 2 * dst_w && src_h == 2 * dst_h) ? 1 : 0;
   for (int base = 0; base < n; base += kMaxPtrBatch) {
     const int m = n - base < kMaxPtrBatch ? n - base : kMaxPtrBatch;
     PtrBatch<const uint8_t> a;
     PtrBatch<uint8_t> b;
     for (int i = 0; i < kMaxPtrBatch; ++i) { a.p[i] = nullptr; b.p[i] = nullptr; }
     for (int i = 0; i < m; ++i) {
-      if (!d_src[base + i] || !d_dst[base + i]) { set_error("stb_resize_bilinear_u8: NULL frame %d", base + i); return STB_ERR_INVALID; }
+      if (!d_src[base + i] || !d_dst[base + i]) { set_error("stb_resize_u8: NULL frame %d", base + i); return STB_ERR_INVALID; }
       a.p[i] = d_src[base + i];
       b.p[i] = d_dst[base + i];
     }
     const dim3 grid(ceil_div(dst_w, 32), ceil_div(dst_h, 8), m);
-    if (channels == 3) stb_launch(resize_linear_u8_kernel<3>, grid, dim3(256), 0, s, a, b, src_w, src_h, dst_w, dst_h, scale_x, scale_y, area2x);
-    else if (channels == 1) stb_launch(resize_linear_u8_kernel<1>, grid, dim3(256), 0, s, a, b, src_w, src_h, dst_w, dst_h, scale_x, scale_y, area2x);
-    else stb_launch(resize_linear_u8_kernel<4>, grid, dim3(256), 0, s, a, b, src_w, src_h, dst_w, dst_h, scale_x, scale_y, area2x);
-    STB_CHECK_LAUNCH("resize_linear_u8_kernel");
+    if (interp == kInterpNearest) STB_RESIZE_DISPATCH(resize_nearest_u8_kernel, src_w, src_h, dst_w, dst_h, scale_x, scale_y);
+    else if (interp == kInterpArea && down && int_scale) STB_RESIZE_DISPATCH(resize_area_int_u8_kernel, src_w, dst_w, dst_h, isx, isy);
+    else if (interp == kInterpArea && down) STB_RESIZE_DISPATCH(resize_area_u8_kernel, src_w, src_h, dst_w, dst_h, scale_x, scale_y);
+    else STB_RESIZE_DISPATCH(resize_linear_u8_kernel, src_w, src_h, dst_w, dst_h, scale_x, scale_y, area2x, interp == kInterpArea ? 1 : 0);
+    STB_CHECK_LAUNCH("resize kernel");
   }
   return STB_OK;
 }

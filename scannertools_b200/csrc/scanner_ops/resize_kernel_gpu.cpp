@@ -88,10 +88,21 @@ class ResizeKernelGPU : public BatchedKernel {
   void new_stream(const std::vector<u8>& args) {
     args_ = ResizeArgsLite();
     if (!parse_resize_args(args, &args_)) RESULT_ERROR(&valid_, "Resize: could not parse ResizeArgs");
-    // the reference falls back to INTER_LINEAR for unknown names; other known modes are not implemented here
-    if (!args_.interpolation.empty() && args_.interpolation != "INTER_LINEAR")
-      RESULT_ERROR(&valid_, "Resize (B200): interpolation %s is not implemented, only INTER_LINEAR",
-                   args_.interpolation.c_str());
+    // resize_kernel.cpp:31-35: names outside its INTERP_TYPES table silently mean INTER_LINEAR.  Of the
+    // names inside the table, INTER_LINEAR / INTER_NEAREST / INTER_AREA are implemented; the rest fail
+    // validate() instead of silently producing a different interpolation.
+    interp_ = 0;
+    const int code = stb_resize_interp_code(args_.interpolation.c_str());
+    if (code >= 0) {
+      interp_ = code;
+    } else {
+      static const char* const kKnownUnimplemented[] = {"INTER_CUBIC", "INTER_LANCZOS4", "INTER_MAX", "WARP_FILL_OUTLIERS",
+                                                        "WARP_INVERSE_MAP"};
+      for (const char* name : kKnownUnimplemented)
+        if (args_.interpolation == name)
+          RESULT_ERROR(&valid_, "Resize (B200): interpolation %s is not implemented (INTER_LINEAR, INTER_NEAREST, INTER_AREA)",
+                       args_.interpolation.c_str());
+    }
   }
 
   void execute(const BatchedElements& input_columns, BatchedElements& output_columns) override {
@@ -111,8 +122,8 @@ class ResizeKernelGPU : public BatchedKernel {
       src_[i] = frame_col[i].as_const_frame()->data;
       dst_[i] = output_frames[i]->data;
     }
-    STB_CHECK(stb_resize_bilinear_u8(src_.data(), input_count, frame->width(), frame->height(), frame->channels(),
-                                     dst_.data(), target_width, target_height, stream_));
+    STB_CHECK(stb_resize_u8(src_.data(), input_count, frame->width(), frame->height(), frame->channels(), dst_.data(),
+                            target_width, target_height, interp_, stream_));
     for (i32 i = 0; i < input_count; ++i) insert_frame(output_columns[0], output_frames[i]);
     CU_CHECK(cudaStreamSynchronize(stream_));
   }
@@ -121,6 +132,7 @@ class ResizeKernelGPU : public BatchedKernel {
   DeviceHandle device_;
   cudaStream_t stream_;
   ResizeArgsLite args_;
+  int interp_ = 0;
   Result valid_;
   std::vector<const uint8_t*> src_;
   std::vector<uint8_t*> dst_;

@@ -190,12 +190,13 @@ def resize_target(frame_w, frame_h, width=0, height=0, min=False, preserve_aspec
 
 def resize(frames, width=0, height=0, min=False, preserve_aspect=False, interpolation='INTER_LINEAR', stream=None):
     """Resize op (scannertools_cpp/imgproc/resize_kernel.cpp:22-105) on uint8 frames: n frames ->
-    [n, height, width, C], bit-exact with cv::resize INTER_LINEAR.  Only the default interpolation
-    is implemented (the reference silently falls back to INTER_LINEAR for unknown names, :31-35)."""
+    [n, height, width, C], bit-exact with cv::resize for INTER_LINEAR (the default), INTER_NEAREST and
+    INTER_AREA; the other names of the reference's table (:9-20) raise NotImplementedError."""
     torch = _torch()
     lib = _lib.load()
-    if interpolation != 'INTER_LINEAR':
-        raise NotImplementedError('Resize: only INTER_LINEAR is implemented (got %r)' % (interpolation,))
+    interp = lib.stb_resize_interp_code((interpolation or '').encode())
+    if interp < 0:
+        raise NotImplementedError('Resize: INTER_LINEAR, INTER_NEAREST and INTER_AREA are implemented (got %r)' % (interpolation,))
     if isinstance(frames, torch.Tensor) and frames.dim() == 3:
         frames = frames.unsqueeze(0)
     lst = [frames[i] for i in range(frames.shape[0])] if isinstance(frames, torch.Tensor) else list(frames)
@@ -211,7 +212,7 @@ def resize(frames, width=0, height=0, min=False, preserve_aspect=False, interpol
     with torch.cuda.device(lst[0].device):
         st = _lib.ptr_table([f.data_ptr() for f in lst])
         dt = _lib.ptr_table([out[i].data_ptr() for i in range(len(lst))])
-        _lib.check(lib.stb_resize_bilinear_u8(st, len(lst), W, H, c, dt, tw, th, _stream_ptr(stream)), lib)
+        _lib.check(lib.stb_resize_u8(st, len(lst), W, H, c, dt, tw, th, interp, _stream_ptr(stream)), lib)
     return out
 
 

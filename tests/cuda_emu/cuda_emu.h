@@ -132,6 +132,7 @@ static inline int __float2int_rn(float a) { return (int)std::nearbyint(a); }
 static inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline int __double2int_rd(double a) { return (int)std::floor(a); }
+static inline int __double2int_ru(double a) { return (int)std::ceil(a); }
 static inline int __double2int_rn(double a) { return (int)std::nearbyint(a); }
 static inline unsigned __vsub4(unsigned a, unsigned b) {
   unsigned r = 0;

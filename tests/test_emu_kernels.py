@@ -155,6 +155,23 @@ def test_emu_resize_bit_exact(emu):
         out = np.zeros((dh, dw, cn), np.uint8)
         assert emu.stb_resize_bilinear_u8(_lib.ptr_table([img.ctypes.data]), 1, sw, sh, cn, _lib.ptr_table([out.ctypes.data]), dw, dh, None) == 0
         assert np.array_equal(out, restate.resize(img, dw, dh)), (sw, sh, dw, dh, cn)
+    # the other interpolation names of ResizeArgs: nearest, area (integer factors, general tables,
+    # up-scaled / mixed axes), 1/3/4 channels, degenerate sizes
+    codes = {n: emu.stb_resize_interp_code(n.encode()) for n in ('INTER_LINEAR', 'INTER_NEAREST', 'INTER_AREA')}
+    assert codes == {'INTER_LINEAR': 0, 'INTER_NEAREST': 1, 'INTER_AREA': 2}
+    assert emu.stb_resize_interp_code(b'') == 0 and emu.stb_resize_interp_code(b'INTER_CUBIC') == -1
+    for (sh, sw, dh, dw) in [(108, 192, 24, 43), (90, 160, 37, 71), (72, 128, 24, 43), (60, 90, 20, 30), (64, 96, 16, 24),
+                             (40, 60, 20, 30), (24, 43, 108, 192), (30, 40, 60, 20), (30, 40, 15, 80), (7, 5, 31, 33),
+                             (33, 47, 1, 1), (1, 1, 5, 7)]:
+        for cn in (1, 3, 4):
+            img = rng.integers(0, 256, (sh, sw, cn), dtype=np.uint8)
+            for name, code in codes.items():
+                out = np.zeros((dh, dw, cn), np.uint8)
+                assert emu.stb_resize_u8(_lib.ptr_table([img.ctypes.data]), 1, sw, sh, cn, _lib.ptr_table([out.ctypes.data]),
+                                         dw, dh, code, None) == 0
+                assert np.array_equal(out, restate.resize(img, dw, dh, name)), (sh, sw, dh, dw, cn, name)
+    img = rng.integers(0, 256, (8, 8, 3), dtype=np.uint8)
+    assert emu.stb_resize_u8(_lib.ptr_table([img.ctypes.data]), 1, 8, 8, 3, _lib.ptr_table([img.ctypes.data]), 4, 4, -1, None) != 0
     w, h = C.c_int(), C.c_int()
     # ResizeArgs semantics of resize_kernel.cpp:43-61
     assert emu.stb_resize_target(1920, 1080, 426, 0, 0, 1, C.byref(w), C.byref(h)) == 0 and (w.value, h.value) == (426, 239)

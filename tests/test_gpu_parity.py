@@ -216,6 +216,18 @@ def test_resize_goldens_and_pipeline_size(torch, ops, golden):
     for i in range(3):
         assert np.array_equal(out[i], (cvo or restate).resize(fr[i], 426, 240)), i
     assert ops.resize_target(1920, 1080, width=426, preserve_aspect=True) == (426, 239)
+    # the other interpolation names: nearest, area (1080p -> 426x240 general tables, -> 480x270 integer
+    # factor 4, -> 960x540 the 2x2 path, up-scaling and mixed axes)
+    for name in ('INTER_NEAREST', 'INTER_AREA'):
+        for (tw, th) in [(426, 240), (480, 270), (960, 540)]:
+            out = ops.resize(dev(torch, fr[:2]), width=tw, height=th, interpolation=name).cpu().numpy()
+            for i in range(2):
+                assert np.array_equal(out[i], (cvo or restate).resize(fr[i], tw, th, name)), (name, tw, th, i)
+    small = np.ascontiguousarray(fr[0, :97, :131])
+    for name in ('INTER_NEAREST', 'INTER_AREA', 'INTER_LINEAR'):
+        for (tw, th) in [(300, 200), (64, 200), (300, 31), (131, 97), (1, 1)]:
+            out = ops.resize(dev(torch, small), width=tw, height=th, interpolation=name).cpu().numpy()[0]
+            assert np.array_equal(out, (cvo or restate).resize(small, tw, th, name)), (name, tw, th)
     with pytest.raises(NotImplementedError):
         ops.resize(dev(torch, fr[:1]), width=10, height=10, interpolation='INTER_CUBIC')
 

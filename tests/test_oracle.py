@@ -144,3 +144,20 @@ def test_cv2_matches_goldens(golden, have_cv2):
     assert np.array_equal(cv2_ops.resize(gr['in_up'], 200, 100), gr['out_up'])
     gs = golden('shot_c1.npz')
     assert cv2_ops.shot_boundaries(list(gs['hists'].reshape(-1, 3, 16))) == list(gs['boundaries'])
+
+
+def test_restate_resize_interpolations_vs_cv2():
+    """INTER_NEAREST / INTER_AREA / INTER_LINEAR of the restatement against cv2 itself on the shapes
+    that reach every OpenCV branch: integer and fractional factors, 2x2, up-scaling, mixed axes,
+    degenerate 1-pixel sizes; 1, 3 and 4 channels."""
+    cv2 = pytest.importorskip('cv2')
+    rng = np.random.default_rng(3)
+    for (sh, sw, dh, dw) in [(108, 192, 24, 43), (90, 160, 37, 71), (54, 96, 50, 90), (72, 128, 24, 43), (60, 90, 20, 30),
+                             (64, 96, 16, 24), (40, 60, 20, 30), (24, 43, 108, 192), (37, 71, 90, 160), (30, 40, 60, 20),
+                             (30, 40, 15, 80), (270, 480, 240, 426), (7, 5, 31, 33), (50, 50, 50, 50), (33, 47, 1, 1), (1, 1, 5, 7)]:
+        for cn in (1, 3, 4):
+            src = rng.integers(0, 256, (sh, sw, cn), dtype=np.uint8)
+            src = src[..., 0] if cn == 1 else src
+            for name in ('INTER_NEAREST', 'INTER_AREA', 'INTER_LINEAR'):
+                ref = cv2.resize(src, (dw, dh), interpolation=getattr(cv2, name))
+                assert np.array_equal(restate.resize(src, dw, dh, name), ref), (sh, sw, dh, dw, cn, name)
