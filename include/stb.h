@@ -104,7 +104,7 @@ typedef struct stb_farneback_params {
   int fast_pyramids;  /* 0    (only 0)                             */
   int win_size;       /* 15   (odd, <= 31)                         */
   int num_iters;      /* 3                                         */
-  int poly_n;         /* 5    (only 5)                             */
+  int poly_n;         /* 5    (3..7; 5 has the tuned kernel)       */
   double poly_sigma;  /* 1.2                                       */
   int flags;          /* 0 = box window (the reference); 256 = cv::OPTFLOW_FARNEBACK_GAUSSIAN
                          (Gaussian window, generic kernel); OPTFLOW_USE_INITIAL_FLOW is not supported */

@@ -43,12 +43,13 @@ def optical_flow(frame0, frame1):
     return _finder.calc(gray(frame0), gray(frame1), None)
 
 
-def optical_flow_params(frame0, frame1, num_levels=3, win_size=15, num_iters=3, flags=0, pyr_scale=0.5):
+def optical_flow_params(frame0, frame1, num_levels=3, win_size=15, num_iters=3, flags=0, pyr_scale=0.5, poly_n=5,
+                        poly_sigma=1.2):
     """The same op with other FarnebackOpticalFlow arguments (flags=256: OPTFLOW_FARNEBACK_GAUSSIAN);
     the reference itself only ever uses FARNEBACK_ARGS."""
     a = FARNEBACK_ARGS
     return cv2.calcOpticalFlowFarneback(gray(frame0), gray(frame1), None, pyr_scale, num_levels, win_size,
-                                        num_iters, a['polyN'], a['polySigma'], flags)
+                                        num_iters, poly_n, poly_sigma, flags)
 
 
 def flow_histogram(flow):

@@ -93,7 +93,7 @@ def poly_consts(n=5, sigma=1.2):
     return g, xg, xxg, ig
 
 
-def farneback(gray0, gray1, dump_level=None, winsize=15, iters=3, levels=3, flags=0, pyr_scale=0.5):
+def farneback(gray0, gray1, dump_level=None, winsize=15, iters=3, levels=3, flags=0, pyr_scale=0.5, poly_n=5, poly_sigma=1.2):
     """Returns flow (HxWx2 f32).  With dump_level=k also returns a dict of level-k
     intermediates: I0, I1 (h x w), R0, R1, M0 (h x w x 5), flow (h x w x 2)."""
     g0 = np.ascontiguousarray(gray0, np.uint8)
@@ -102,7 +102,7 @@ def farneback(gray0, gray1, dump_level=None, winsize=15, iters=3, levels=3, flag
     out = np.empty((H, W, 2), np.float32)
     if dump_level is None:
         lib().orc_farneback_flags(_p(g0), _p(g1), C.c_int(W), C.c_int(H), _p(out), C.c_int(levels), C.c_double(pyr_scale),
-                                  C.c_int(winsize), C.c_int(iters), C.c_int(5), C.c_double(1.2), C.c_int(flags), None)
+                                  C.c_int(winsize), C.c_int(iters), C.c_int(poly_n), C.c_double(poly_sigma), C.c_int(flags), None)
         return out
     w, h = pyramid_info(W, H)[dump_level]
     d = dict(I0=np.empty((h, w), np.float32), I1=np.empty((h, w), np.float32),

@@ -34,8 +34,9 @@ constexpr int kMaxScales = 4;     // numLevels = 3 -> up to 4 scales (Appendix A
 constexpr int kMaxGaussTaps = 19; // sigma 3.5 -> ksize 19
 constexpr int kPolyN = 5;
 
+constexpr int kMaxPolyN = 7;   // polyN = 5 (the reference) has the tiled kernel; 3..7 run a generic one
 struct PolyConsts {
-  float g[kPolyN + 1], xg[kPolyN + 1], xxg[kPolyN + 1];
+  float g[kMaxPolyN + 1], xg[kMaxPolyN + 1], xxg[kMaxPolyN + 1];
   float ig11, ig03, ig33, ig55;
 };
 
@@ -483,6 +484,51 @@ polyexp_kernel(const float* __restrict__ I, float* __restrict__ R, int w, int h,
         if (x + i < w) { d0[i] = o0[i]; d0[n + i] = o1[i]; d0[2 * n + i] = o2[i]; d0[3 * n + i] = o3[i]; d0[4 * n + i] = o4[i]; }
     }
   }
+}
+
+// Generic polynomial expansion for polyN != 5 (not used by the reference, which hard-codes 5):
+// one thread per pixel, the (2n+1)^2 neighbourhood read straight from global memory (L1/L2
+// resident), same arithmetic as polyexp_kernel.  Correctness path, not tuned.
+__device__ __forceinline__ void polyexp_column(const float* __restrict__ src, int w, int h, int xc, int y, int n,
+                                               const PolyConsts& c, float& r0, float& r1, float& r2) {
+  const float s0 = __ldg(src + y * w + xc);
+  r0 = s0 * c.g[0]; r1 = 0.f; r2 = 0.f;
+  for (int k = 1; k <= n; ++k) {
+    const float a = __ldg(src + max(y - k, 0) * w + xc), b = __ldg(src + min(y + k, h - 1) * w + xc);
+    const float pp = a + b;
+    r0 = fmaf(c.g[k], pp, r0);
+    r1 = fmaf(c.xg[k], b - a, r1);
+    r2 = fmaf(c.xxg[k], pp, r2);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+polyexp_generic_kernel(const float* __restrict__ I, float* __restrict__ R, int w, int h, PolyConsts c, int n, int frame0) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= w || y >= h) return;
+  const int frame = frame0 + blockIdx.z;
+  const int npx = w * h;
+  const float* src = I + (size_t)frame * npx;
+  float* dst = R + (size_t)frame * 5 * npx + y * w + x;
+  float c0, c1, c2;
+  polyexp_column(src, w, h, x, y, n, c, c0, c1, c2);
+  float b1 = c0 * c.g[0], b2 = 0.f, b3 = c1 * c.g[0], b4 = 0.f, b5 = c2 * c.g[0], b6 = 0.f;
+  for (int k = 1; k <= n; ++k) {
+    float p0, p1, p2, m0, m1, m2;
+    polyexp_column(src, w, h, min(x + k, w - 1), y, n, c, p0, p1, p2);
+    polyexp_column(src, w, h, max(x - k, 0), y, n, c, m0, m1, m2);
+    b1 = fmaf(p0 + m0, c.g[k], b1);
+    b4 = fmaf(p0 + m0, c.xxg[k], b4);
+    b2 = fmaf(p0 - m0, c.xg[k], b2);
+    b3 = fmaf(p1 + m1, c.g[k], b3);
+    b6 = fmaf(p1 - m1, c.xg[k], b6);
+    b5 = fmaf(p2 + m2, c.g[k], b5);
+  }
+  dst[0] = b3 * c.ig11;                          // d/dy
+  dst[npx] = b2 * c.ig11;                        // d/dx
+  dst[2 * npx] = fmaf(b1, c.ig03, b5 * c.ig33);  // yy
+  dst[3 * npx] = fmaf(b1, c.ig03, b4 * c.ig33);  // xx
+  dst[4 * npx] = b6 * c.ig55;                    // xy
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1315,7 +1361,7 @@ static bool invert_spd6(double A[6][6], double inv[6][6]) {
 
 static bool poly_consts(int n, double sigma, PolyConsts* pc) {
   // FarnebackPrepareGaussian (Appendix A.3)
-  float gf[2 * kPolyN + 1];
+  float gf[2 * kMaxPolyN + 1];
   if (sigma < 1.1920929e-07) sigma = n * 0.3;
   double s = 0;
   for (int x = -n; x <= n; ++x) { gf[x + n] = (float)std::exp(-x * x / (2 * sigma * sigma)); s += gf[x + n]; }
@@ -1348,7 +1394,7 @@ constexpr int kFlagGaussian = 256;   // cv::OPTFLOW_FARNEBACK_GAUSSIAN
 static int validate_params(const stb_farneback_params& p) {
   if (p.num_levels < 0 || p.num_levels > kMaxScales - 1 || !(p.pyr_scale >= 0.5 && p.pyr_scale < 1.0) || p.fast_pyramids != 0 ||
       p.win_size < 3 || (p.win_size & 1) == 0 || p.win_size > 2 * kItMaxHalo + 1 || p.num_iters < 1 ||
-      p.poly_n != kPolyN || (p.flags & ~kFlagGaussian) != 0) {
+      p.poly_n < 3 || p.poly_n > kMaxPolyN || (p.flags & ~kFlagGaussian) != 0) {
     set_error("stb_farneback: unsupported parameters (levels=%d pyr_scale=%g fast=%d win=%d iters=%d poly_n=%d flags=%d)",
               p.num_levels, p.pyr_scale, p.fast_pyramids, p.win_size, p.num_iters, p.poly_n, p.flags);
     return STB_ERR_UNSUPPORTED;
@@ -1683,8 +1729,12 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
                      (const uint8_t*)h->gray, h->I, pp, fa);
           STB_CHECK_LAUNCH("pyr_kernel");
         }
-        stb_launch(polyexp_kernel, dim3(ceil_div(w, kPeTW), ceil_div(hh, kPeTH), fb - fa), dim3(kPeThreads), 0, s,
-                   (const float*)h->I, h->R, w, hh, h->pc, fa);
+        if (h->prm.poly_n == kPolyN)
+          stb_launch(polyexp_kernel, dim3(ceil_div(w, kPeTW), ceil_div(hh, kPeTH), fb - fa), dim3(kPeThreads), 0, s,
+                     (const float*)h->I, h->R, w, hh, h->pc, fa);
+        else
+          stb_launch(polyexp_generic_kernel, dim3(ceil_div(w, 32), ceil_div(hh, 8), fb - fa), dim3(256), 0, s,
+                     (const float*)h->I, h->R, w, hh, h->pc, h->prm.poly_n, fa);
         STB_CHECK_LAUNCH("polyexp_kernel");
         frames_done = fb;
       }

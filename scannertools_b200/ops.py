@@ -250,9 +250,9 @@ class OpticalFlow:
     OPTFLOW_FARNEBACK_GAUSSIAN = 256
 
     def __init__(self, width, height, max_batch=16, device=None, num_levels=3, win_size=15, num_iters=3, flags=0,
-                 pyr_scale=0.5):
+                 pyr_scale=0.5, poly_n=5, poly_sigma=1.2):
         """The keyword defaults are the reference's hard-coded FarnebackOpticalFlow arguments
-        (optical_flow_kernel_cpu.cpp:16).  Other pyramid depths (<= 3), 0.5 <= pyr_scale < 1, odd windows <= 31, iteration
+        (optical_flow_kernel_cpu.cpp:16).  Other pyramid depths (<= 3), 0.5 <= pyr_scale < 1, odd windows <= 31, polyN 3..7, iteration
         counts and flags=OPTFLOW_FARNEBACK_GAUSSIAN run on the generic kernels; anything else
         raises StbError (STB_ERR_UNSUPPORTED)."""
         torch = _torch()
@@ -260,7 +260,8 @@ class OpticalFlow:
         self.width, self.height, self.max_batch = int(width), int(height), int(max_batch)
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self._h = C.c_void_p()
-        prm = _lib.FarnebackParams(int(num_levels), float(pyr_scale), 0, int(win_size), int(num_iters), 5, 1.2, int(flags))
+        prm = _lib.FarnebackParams(int(num_levels), float(pyr_scale), 0, int(win_size), int(num_iters), int(poly_n),
+                                   float(poly_sigma), int(flags))
         with torch.cuda.device(self.device):
             _lib.check(self._lib.stb_farneback_create(self.width, self.height, self.max_batch, C.byref(prm), C.byref(self._h)), self._lib)
 

@@ -223,15 +223,16 @@ def test_emu_fused_hsv_histogram(emu, golden):
     assert emu.stb_hist_hsv16(_lib.ptr_table([fr.ctypes.data]), 1, 23, 17, emu.stb_color_code(b'COLOR_RGB2GRAY'), P(out), None) != 0
 
 
-@pytest.mark.parametrize('levels,iters,win,flags,ps', [(0, 1, 15, 0, 0.5), (1, 1, 15, 0, 0.5), (2, 4, 15, 0, 0.5), (3, 3, 5, 0, 0.5),
-                                                       (3, 3, 15, 256, 0.5), (2, 2, 9, 256, 0.5), (3, 3, 15, 0, 0.75)])
-def test_emu_farneback_parameter_combinations(emu, levels, iters, win, flags, ps):
+@pytest.mark.parametrize('levels,iters,win,flags,ps,pn,sig', [
+    (0, 1, 15, 0, 0.5, 5, 1.2), (1, 1, 15, 0, 0.5, 5, 1.2), (2, 4, 15, 0, 0.5, 5, 1.2), (3, 3, 5, 0, 0.5, 5, 1.2),
+    (3, 3, 15, 256, 0.5, 5, 1.2), (2, 2, 9, 256, 0.5, 5, 1.2), (3, 3, 15, 0, 0.75, 5, 1.2), (3, 3, 15, 0, 0.5, 7, 1.5)])
+def test_emu_farneback_parameter_combinations(emu, levels, iters, win, flags, ps, pn, sig):
     """stb_farneback_params other than the reference's defaults: fewer pyramid levels, a single
-    iteration (only the last-iteration kernel runs), more iterations, another window, and the
-    Gaussian window (flags = cv::OPTFLOW_FARNEBACK_GAUSSIAN)."""
+    iteration (only the last-iteration kernel runs), more iterations, another window, the
+    Gaussian window (flags = cv::OPTFLOW_FARNEBACK_GAUSSIAN), another pyramid scale, polyN = 7."""
     h, w = 96, 128
     clip = synth.textured_clip(9, 2, h, w)
-    prm = _lib.FarnebackParams(levels, ps, 0, win, iters, 5, 1.2, flags)
+    prm = _lib.FarnebackParams(levels, ps, 0, win, iters, pn, sig, flags)
     hd = C.c_void_p()
     assert emu.stb_farneback_create(w, h, 1, C.byref(prm), C.byref(hd)) == 0
     out = np.zeros((h, w, 2), np.float32)
@@ -239,13 +240,13 @@ def test_emu_farneback_parameter_combinations(emu, levels, iters, win, flags, ps
                                  _lib.ptr_table([out.ctypes.data]), None) == 0
     emu.stb_farneback_destroy(hd)
     ref = restate.farneback(restate.gray(clip[0]), restate.gray(clip[1]), winsize=win, iters=iters, levels=levels, flags=flags,
-                            pyr_scale=ps)
+                            pyr_scale=ps, poly_n=pn, poly_sigma=sig)
     e = epe(out, ref)
-    assert e.max() < 1e-4, (levels, iters, win, flags, ps, e.max())
+    assert e.max() < 1e-4, (levels, iters, win, flags, ps, pn, e.max())
     if flags == 0 and (levels, iters, win) == (0, 1, 15):
         for bad in (_lib.FarnebackParams(levels, 0.5, 0, win, iters, 5, 1.2, 4),     # OPTFLOW_USE_INITIAL_FLOW
                     _lib.FarnebackParams(levels, 0.3, 0, win, iters, 5, 1.2, 0),     # pyr_scale < 0.5
-                    _lib.FarnebackParams(levels, 0.5, 0, win, iters, 7, 1.5, 0)):    # polyN 7
+                    _lib.FarnebackParams(levels, 0.5, 0, win, iters, 9, 1.5, 0)):    # polyN > 7
             assert emu.stb_farneback_create(w, h, 1, C.byref(bad), C.byref(hd)) != 0
 
 

@@ -349,24 +349,27 @@ def test_farneback_parity_sizes(torch, ops, h, w, seed):
     of.close()
 
 
-@pytest.mark.parametrize('levels,win,iters,flags,ps', [(3, 15, 3, 256, 0.5), (2, 9, 2, 256, 0.5), (3, 21, 3, 0, 0.5), (1, 15, 1, 0, 0.5),
-                                                       (3, 7, 4, 0, 0.5), (3, 15, 3, 0, 0.75), (2, 15, 3, 256, 0.6)])
-def test_farneback_other_parameters(torch, ops, levels, win, iters, flags, ps):
+@pytest.mark.parametrize('levels,win,iters,flags,ps,pn,sig', [
+    (3, 15, 3, 256, 0.5, 5, 1.2), (2, 9, 2, 256, 0.5, 5, 1.2), (3, 21, 3, 0, 0.5, 5, 1.2), (1, 15, 1, 0, 0.5, 5, 1.2),
+    (3, 7, 4, 0, 0.5, 5, 1.2), (3, 15, 3, 0, 0.75, 5, 1.2), (2, 15, 3, 256, 0.6, 5, 1.2), (3, 15, 3, 0, 0.5, 7, 1.5)])
+def test_farneback_other_parameters(torch, ops, levels, win, iters, flags, ps, pn, sig):
     """FarnebackOpticalFlow arguments other than the reference's (generic kernels): the Gaussian
     window (OPTFLOW_FARNEBACK_GAUSSIAN), other windows / depths / iteration counts -- against cv2
     with the same arguments (or the pinned restatement when cv2 is missing)."""
     h, w = 270, 480
     clip = synth.textured_clip(11, 3, h, w)
-    of = ops.OpticalFlow(w, h, max_batch=2, num_levels=levels, win_size=win, num_iters=iters, flags=flags, pyr_scale=ps)
+    of = ops.OpticalFlow(w, h, max_batch=2, num_levels=levels, win_size=win, num_iters=iters, flags=flags, pyr_scale=ps,
+                         poly_n=pn, poly_sigma=sig)
     out, fh = of.execute_with_histogram(dev(torch, clip))
     out, fh = out.cpu().numpy(), fh.cpu().numpy()
     for i in range(2):
         if cvo:
-            ref = cvo.optical_flow_params(clip[i], clip[i + 1], num_levels=levels, win_size=win, num_iters=iters, flags=flags, pyr_scale=ps)
+            ref = cvo.optical_flow_params(clip[i], clip[i + 1], num_levels=levels, win_size=win, num_iters=iters, flags=flags, pyr_scale=ps,
+                                          poly_n=pn, poly_sigma=sig)
         else:
             ref = restate.farneback(restate.gray(clip[i]), restate.gray(clip[i + 1]), winsize=win, iters=iters, levels=levels, flags=flags,
-                                    pyr_scale=ps)
-        check_flow(out[i], ref, (levels, win, iters, flags, ps, i))
+                                    pyr_scale=ps, poly_n=pn, poly_sigma=sig)
+        check_flow(out[i], ref, (levels, win, iters, flags, ps, pn, i))
         assert np.array_equal(fh[i], o_flow_hist(out[i])), i          # the (unfused here) histogram of the flow produced
     of.close()
     from scannertools_b200 import _lib

@@ -43,18 +43,20 @@ def test_restate_farneback(golden):
         assert e.mean() < 1e-5 and e.max() < 1e-4, (c, e.mean(), e.max())
 
 
-@pytest.mark.parametrize('win,iters,levels,flags,ps', [(15, 3, 3, 256, 0.5), (9, 2, 2, 256, 0.5), (21, 3, 3, 0, 0.5), (15, 3, 3, 0, 0.75)])
-def test_restate_farneback_other_parameters_vs_cv2(win, iters, levels, flags, ps):
+@pytest.mark.parametrize('win,iters,levels,flags,ps,pn,sig', [(15, 3, 3, 256, 0.5, 5, 1.2), (9, 2, 2, 256, 0.5, 5, 1.2), (21, 3, 3, 0, 0.5, 5, 1.2),
+                                                              (15, 3, 3, 0, 0.75, 5, 1.2), (15, 3, 3, 0, 0.5, 7, 1.5), (15, 3, 3, 0, 0.5, 3, 1.0)])
+def test_restate_farneback_other_parameters_vs_cv2(win, iters, levels, flags, ps, pn, sig):
     """Window sizes / iteration counts / the Gaussian window (OPTFLOW_FARNEBACK_GAUSSIAN) of the
     restatement, checked against cv2 itself (these are not used by the reference, so no golden)."""
     cv2_ops = pytest.importorskip('oracle.cv2_ops')
     from scannertools_b200 import synth
     clip = synth.textured_clip(1, 2, 120, 160)
-    ref = cv2_ops.optical_flow_params(clip[0], clip[1], num_levels=levels, win_size=win, num_iters=iters, flags=flags, pyr_scale=ps)
+    ref = cv2_ops.optical_flow_params(clip[0], clip[1], num_levels=levels, win_size=win, num_iters=iters, flags=flags, pyr_scale=ps,
+                                      poly_n=pn, poly_sigma=sig)
     fl = restate.farneback(restate.gray(clip[0]), restate.gray(clip[1]), winsize=win, iters=iters, levels=levels, flags=flags,
-                           pyr_scale=ps)
+                           pyr_scale=ps, poly_n=pn, poly_sigma=sig)
     e = epe(fl, ref)
-    assert e.mean() < 1e-5 and e.max() < 1e-4, (win, iters, levels, flags, e.mean(), e.max())
+    assert e.mean() < 1e-5 and e.max() < 1e-4, (win, iters, levels, flags, ps, pn, e.mean(), e.max())
 
 
 def test_restate_pyramid_geometry():
