@@ -56,3 +56,18 @@ def test_product_never_imports_oracle():
             if f.endswith(('.py', '.cu', '.h', '.cpp', '.cuh')):
                 txt = open(os.path.join(dirpath, f), errors='replace').read()
                 assert 'import oracle' not in txt and 'from oracle' not in txt and 'cuda_emu.h"' not in txt.replace('#include "cuda_emu.h"\n#else', ''), f
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/stb.h must compile as C99 on its own (no C++, no CUDA or
+    torch types in the signatures)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('no gcc')
+    hdr = os.path.join(ROOT, 'include', 'stb.h')
+    r = subprocess.run([gcc, '-x', 'c', '-std=c99', '-fsyntax-only', '-Wall', '-Werror', hdr], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    code = re.sub(r'/\*.*?\*/', '', open(hdr).read(), flags=re.S)       # declarations only, comments stripped
+    assert 'torch' not in code and 'cudaStream_t' not in code and 'std::' not in code and '#include <cuda' not in code
