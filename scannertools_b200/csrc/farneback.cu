@@ -1013,6 +1013,28 @@ __device__ __forceinline__ void iter15_global_phase(const float2* fl, unsigned* 
   }
 }
 
+// 2x2 solve of the winSize-15 kernels on the UN-normalised window sums: the 1/225 factors of
+// OpenCV's g = sum * scale cancel between numerator and determinant, only its +1e-3 scales by
+// 225^2.  Differences of products carry the rounding error of one product through an FMA;
+// the reciprocal is MUFU.RCP (1 ulp), 1.2e-7 relative on the flow.  Saves the five scalings and
+// the ~10-instruction IEEE division per pixel (level-0 update launch 535 -> 525 us).
+__device__ __forceinline__ float2 solve_flow15(float g11, float g12, float g22, float h1, float h2) {
+  const float w12 = g12 * g12;
+  const float det = fmaf(g11, g22, -w12) + fmaf(-g12, g12, w12);
+  const float den = det + 1e-3f * 225.f * 225.f;
+  float idet;
+#ifdef STB_CPU_EMU
+  idet = 1.f / den;
+#else
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(idet) : "f"(den));
+#endif
+  const float t1 = g12 * h1;
+  const float nx = fmaf(g11, h2, -t1) + fmaf(-g12, h1, t1);
+  const float t2 = g12 * h2;
+  const float ny = fmaf(g22, h1, -t2) + fmaf(-g12, h2, t2);
+  return make_float2(nx * idet, ny * idet);
+}
+
 template <bool UPDATE, bool HIST>
 __global__ void __launch_bounds__(kFiThreads, 4)
 iter15_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const float* __restrict__ R,
@@ -1078,20 +1100,9 @@ iter15_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const flo
     // Vt[c&1] is next written for plane c+2, after the barrier of plane c+1: safe.
   }
 
-  const float inv_area = 1.f / 225.f;
 #pragma unroll
-  for (int i = 0; i < kFiGC; ++i) {
-    const float g11 = sums[0][i] * inv_area, g12 = sums[1][i] * inv_area, g22 = sums[2][i] * inv_area;
-    const float h1 = sums[3][i] * inv_area, h2 = sums[4][i] * inv_area;
-    const float w12 = g12 * g12;
-    const float det = fmaf(g11, g22, -w12) + fmaf(-g12, g12, w12);
-    const float idet = 1.f / (det + 1e-3f);
-    const float t1 = g12 * h1;
-    const float nx = fmaf(g11, h2, -t1) + fmaf(-g12, h1, t1);
-    const float t2 = g12 * h2;
-    const float ny = fmaf(g22, h1, -t2) + fmaf(-g12, h2, t2);
-    fl[lane * kFiFlStride + warp * kFiGC + i] = make_float2(nx * idet, ny * idet);
-  }
+  for (int i = 0; i < kFiGC; ++i)
+    fl[lane * kFiFlStride + warp * kFiGC + i] = solve_flow15(sums[0][i], sums[1][i], sums[2][i], sums[3][i], sums[4][i]);
   __syncthreads();
 
   iter15_global_phase<UPDATE, HIST>(fl, fh, Mout, R, flow_out, flow_hist, w, h, pair, ox0, oy0);
@@ -1251,20 +1262,9 @@ iter15_tma_kernel(const STB_GRID_CONSTANT TmaMap3D map_in, float* __restrict__ M
   }
   __syncthreads();   // every read of raw (plane 4 lives in stage 0) is done before fl aliases it
 
-  const float inv_area = 1.f / 225.f;
 #pragma unroll
-  for (int i = 0; i < kFiGC; ++i) {
-    const float g11 = sums[0][i] * inv_area, g12 = sums[1][i] * inv_area, g22 = sums[2][i] * inv_area;
-    const float h1 = sums[3][i] * inv_area, h2 = sums[4][i] * inv_area;
-    const float w12 = g12 * g12;
-    const float det = fmaf(g11, g22, -w12) + fmaf(-g12, g12, w12);
-    const float idet = 1.f / (det + 1e-3f);
-    const float t1 = g12 * h1;
-    const float nx = fmaf(g11, h2, -t1) + fmaf(-g12, h1, t1);
-    const float t2 = g12 * h2;
-    const float ny = fmaf(g22, h1, -t2) + fmaf(-g12, h2, t2);
-    fl[lane * kFiFlStride + warp * kFiGC + i] = make_float2(nx * idet, ny * idet);
-  }
+  for (int i = 0; i < kFiGC; ++i)
+    fl[lane * kFiFlStride + warp * kFiGC + i] = solve_flow15(sums[0][i], sums[1][i], sums[2][i], sums[3][i], sums[4][i]);
   __syncthreads();
 
   iter15_global_phase<UPDATE, HIST>(fl, fh, Mout, R, flow_out, flow_hist, w, h, pair, ox0, oy0);
