@@ -101,7 +101,7 @@ STB_API int stb_frame_diff(const uint8_t* d_prev, const uint8_t* d_cur, uint8_t*
 typedef struct stb_farneback_params {
   int num_levels;     /* 3   */
   double pyr_scale;   /* 0.5  (0.5 <= pyr_scale < 1)               */
-  int fast_pyramids;  /* 0    (only 0)                             */
+  int fast_pyramids;  /* 0    (0 or 1; no effect, exactly as in OpenCV's CPU implementation, which is the parity target) */
   int win_size;       /* 15   (odd, <= 31)                         */
   int num_iters;      /* 3                                         */
   int poly_n;         /* 5    (3..7; 5 has the tuned kernel)       */

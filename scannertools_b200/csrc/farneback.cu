@@ -1392,7 +1392,7 @@ static bool poly_consts(int n, double sigma, PolyConsts* pc) {
 constexpr int kFlagGaussian = 256;   // cv::OPTFLOW_FARNEBACK_GAUSSIAN
 
 static int validate_params(const stb_farneback_params& p) {
-  if (p.num_levels < 0 || p.num_levels > kMaxScales - 1 || !(p.pyr_scale >= 0.5 && p.pyr_scale < 1.0) || p.fast_pyramids != 0 ||
+  if (p.num_levels < 0 || p.num_levels > kMaxScales - 1 || !(p.pyr_scale >= 0.5 && p.pyr_scale < 1.0) || (p.fast_pyramids != 0 && p.fast_pyramids != 1) ||
       p.win_size < 3 || (p.win_size & 1) == 0 || p.win_size > 2 * kItMaxHalo + 1 || p.num_iters < 1 ||
       p.poly_n < 3 || p.poly_n > kMaxPolyN || (p.flags & ~kFlagGaussian) != 0) {
     set_error("stb_farneback: unsupported parameters (levels=%d pyr_scale=%g fast=%d win=%d iters=%d poly_n=%d flags=%d)",

@@ -494,7 +494,7 @@ def test_c_abi_error_behaviour_on_device(torch, ops):
     assert lib.stb_farneback_run(of._h, bad, 2, ot, None) == -1 and b'NULL' in lib.stb_last_error()
     assert lib.stb_farneback_run(of._h, ft, 0, ot, None) == 0    # empty batch is a no-op
     assert lib.stb_hist_rgb16_strided(C.c_void_p(fr.data_ptr()), 10, 2, 160, 120, C.c_void_p(out.data_ptr()), None) == -1  # stride < frame
-    prm = _lib.FarnebackParams(3, 0.5, 1, 15, 3, 5, 1.2, 0)       # fastPyramids: not implemented
+    prm = _lib.FarnebackParams(3, 0.5, 0, 15, 3, 5, 1.2, 4)       # OPTFLOW_USE_INITIAL_FLOW: not implemented (the op has no flow input)
     h = C.c_void_p()
     assert lib.stb_farneback_create(160, 120, 1, C.byref(prm), C.byref(h)) == -4 and not h.value
     pipe = ops.Pipe(160, 120, max_batch=2, want_flow=False)

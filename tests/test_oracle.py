@@ -163,3 +163,15 @@ def test_restate_resize_interpolations_vs_cv2():
             for name in ('INTER_NEAREST', 'INTER_AREA', 'INTER_LINEAR'):
                 ref = cv2.resize(src, (dw, dh), interpolation=getattr(cv2, name))
                 assert np.array_equal(restate.resize(src, dw, dh, name), ref), (sh, sw, dh, dw, cn, name)
+
+
+def test_cv2_fast_pyramids_is_a_no_op_on_cpu():
+    """stb_farneback_params.fast_pyramids is accepted and ignored: OpenCV's CPU Farneback (the
+    parity target) gives bit-identical flow with fastPyramids true or false."""
+    cv2 = pytest.importorskip('cv2')
+    from scannertools_b200 import synth
+    clip = synth.textured_clip(1, 2, 120, 160)
+    g = [cv2.cvtColor(f, cv2.COLOR_BGR2GRAY) for f in clip]
+    a = cv2.FarnebackOpticalFlow_create(3, 0.5, False, 15, 3, 5, 1.2, 0).calc(g[0], g[1], None)
+    b = cv2.FarnebackOpticalFlow_create(3, 0.5, True, 15, 3, 5, 1.2, 0).calc(g[0], g[1], None)
+    assert np.array_equal(a, b)
