@@ -698,7 +698,9 @@ __device__ __forceinline__ float2 upsample_flow(const float2* __restrict__ fc, i
 // Two horizontally adjacent pixels per thread (8-byte accesses of R0 / M when w is even).  This
 // kernel is DRAM-bound (69 % of peak): the vertical-pair mapping that helps the L1-bound iteration
 // kernel measured 12 % slower here (495 vs 440 us per 16-pair level-0 launch).
-__global__ void __launch_bounds__(256)
+// 5 blocks/SM (48 registers, no spills): with the prefetch-ahead in place the extra resident warps are
+// worth +1 % of the step (before it, 5 blocks/SM measured slower: 500 vs 440 us in isolation).
+__global__ void __launch_bounds__(256, 5)
 updmat_init_kernel(const float* __restrict__ R, const float* __restrict__ flow_coarse, float* __restrict__ M,
                    int w, int h, int wc, int hc, double scale_x, double scale_y, float flow_mul, int pair0,
                    const STB_GRID_CONSTANT TmaMap3D map_R, int prefetch_rows) {
@@ -1740,7 +1742,7 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
       }
       (void)F;
       {
-        // prefetch distance: two resident waves (4 blocks/SM) expressed in block rows
+        // prefetch distance: about two resident waves expressed in block rows
         const int bx = ceil_div(w, 64);
         int ahead = h->prefetch_Ri[k] ? ceil_div(2 * 4 * num_sms(), bx) : 0;
         if (const char* env = getenv("STB_INIT_PREFETCH_WAVES")) ahead = h->prefetch_Ri[k] ? ceil_div(atoi(env) * 4 * num_sms(), bx) : 0;
