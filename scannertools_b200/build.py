@@ -74,6 +74,8 @@ def build_scanner_ops(force=False, scanner_include=None):
            '-L', os.path.join(cuda_home, 'lib64'), '-lcudart']
     if scanner_include is not None:
         cmd.insert(1, '-DSTB_SKIP_OP_DECLARATIONS')
+    else:
+        cmd.insert(1, '-DSTB_COMPAT_SHIM')    # the stb_shim_* test hooks exist only in the compat build
     subprocess.check_call(cmd)
     return OPS_OUT
 

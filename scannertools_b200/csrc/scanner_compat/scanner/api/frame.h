@@ -30,13 +30,14 @@ class FrameInfo {
 // frames are packed row-major HWC with no row pitch (blur_kernel_cpu.cpp:70)
 class Frame {
  public:
-  Frame(FrameInfo info, u8* buffer) : data(buffer), info_(info) {}
+  Frame(FrameInfo info, u8* buffer) : data(buffer), type(info.type), info_(info) {}
   FrameInfo as_frame_info() const { return info_; }
   int height() const { return info_.height(); }
   int width() const { return info_.width(); }
   int channels() const { return info_.channels(); }
   size_t size() const { return info_.size(); }
   u8* data;
+  FrameType type;   // resize_kernel.cpp:64 reads frame->type
 
  private:
   FrameInfo info_;

@@ -19,8 +19,14 @@ inline u8* new_block_buffer_size(DeviceHandle device, size_t element_size, i32 r
 Frame* new_frame(DeviceHandle device, FrameInfo info);
 std::vector<Frame*> new_frames(DeviceHandle device, FrameInfo info, i32 num);
 
+// batched kernels append to a column (histogram_kernel_cpu.cpp:44, resize_kernel.cpp:83) ...
 inline void insert_frame(Elements& column, Frame* frame) { column.push_back(Element(frame)); }
 inline void insert_element(Elements& column, u8* buffer, size_t size) { column.push_back(Element(buffer, size)); }
+// ... non-batched kernels fill the ONE pre-sized slot of each output column: `output_columns` is an
+// Elements with one Element per column (blur_kernel_cpu.cpp:79, optical_flow_kernel_cpu.cpp:42,
+// frame_difference_kernel_cpu.cpp:64)
+inline void insert_frame(Element& element, Frame* frame) { element = Element(frame); }
+inline void insert_element(Element& element, u8* buffer, size_t size) { element = Element(buffer, size); }
 
 void memcpy_buffer(u8* dst, DeviceHandle dst_device, const u8* src, DeviceHandle src_device, size_t size);
 

@@ -178,11 +178,11 @@ SHIM_API int stb_shim_frame_difference(const uint8_t* h_prev, const uint8_t* h_c
   FrameInfo info(h, w, c, FrameType::U8);
   DeviceFrames a(dev, h_prev, 1, info), b(dev, h_cur, 1, info);
   StenciledElements input(1);
-  Elements output;
+  Elements output(1);                 // the engine pre-sizes one Element per output column
   input[0].push_back(Element(a.frames[0]));
   input[0].push_back(Element(b.frames[0]));
   k->execute(input, output);
-  if (output.size() != 1) return -2;
+  if (output.size() != 1 || output[0].is_null()) return -2;
   Frame* f = output[0].as_frame();
   CU_CHECK(cudaMemcpy(h_out, f->data, info.size(), cudaMemcpyDeviceToHost));
   delete_buffer(dev, f->data);

@@ -69,6 +69,10 @@ class ConvertColorKernelGPU : public BatchedKernel {
     CU_CHECK(cudaSetDevice(device_.id));
     const Frame* frame = frame_col[0].as_const_frame();
     const i32 input_count = (i32)num_rows(frame_col);
+    if (frame->type != FrameType::U8 || frame->channels() != 3) {
+      // every conversion implemented here (convert_color_kernel.cpp:19-25,61) reads packed 3-channel bytes
+      STB_FATAL("ConvertColor (B200): only 3-channel U8 frames are implemented");
+    }
     FrameInfo info(frame->height(), frame->width(), stb_color_out_channels(code_), FrameType::U8);
     std::vector<Frame*> output_frames = new_frames(device_, info, input_count);
     src_.resize(input_count);
@@ -110,6 +114,7 @@ REGISTER_KERNEL(ConvertColor, ConvertColorKernelGPU).device(DeviceType::GPU).bat
 REGISTER_KERNEL(ConvertToHSVCPP, ConvertToHSVKernelGPU).device(DeviceType::GPU).batch().num_devices(1);
 
 // test harness hook (compat build only)
+#ifdef STB_COMPAT_SHIM
 extern "C" __attribute__((visibility("default"))) int stb_shim_convert_color(const uint8_t* h_frames, int n, int w, int h,
                                                                              const uint8_t* args, int args_len,
                                                                              uint8_t* h_out, int* out_channels, int device_id) {
@@ -142,4 +147,5 @@ extern "C" __attribute__((visibility("default"))) int stb_shim_convert_color(con
   for (Frame* f : in) delete f;
   return rc;
 }
+#endif  // STB_COMPAT_SHIM
 }  // namespace scanner

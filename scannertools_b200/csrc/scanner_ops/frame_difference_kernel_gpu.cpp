@@ -34,9 +34,13 @@ class FrameDifferenceKernelGPU : public StenciledKernel, public VideoKernel {
     const Frame* secondary = frame_col[0].as_const_frame();   // t-1
     const Frame* primary = frame_col[1].as_const_frame();     // t
     FrameInfo info = primary->as_frame_info();
+    if (secondary->as_frame_info() != info || primary->type != FrameType::U8) {
+      // the subtraction is defined on bytes (frame_difference_kernel_cpu.cpp:51-61 reads u8)
+      STB_FATAL("FrameDifference (B200): both frames must be U8 with one FrameInfo");
+    }
     Frame* output_frame = new_frame(device_, info);
     STB_CHECK(stb_frame_diff(secondary->data, primary->data, output_frame->data, info.size(), stream_));
-    insert_frame(output_columns, output_frame);
+    insert_frame(output_columns[0], output_frame);   // one pre-sized slot per output column (frame_difference_kernel_cpu.cpp:64)
     CU_CHECK(cudaStreamSynchronize(stream_));
   }
 

@@ -114,7 +114,13 @@ class ResizeKernelGPU : public BatchedKernel {
     STB_CHECK(stb_resize_target(frame->width(), frame->height(), args_.width, args_.height, args_.min ? 1 : 0,
                                 args_.preserve_aspect ? 1 : 0, &target_width, &target_height));
     const i32 input_count = (i32)num_rows(frame_col);
-    FrameInfo info(target_height, target_width, frame->channels(), FrameType::U8);
+    const int ch = frame->channels();
+    if (frame->type != FrameType::U8 || !(ch == 1 || ch == 3 || ch == 4)) {
+      // resize_kernel.cpp:64 propagates frame->type to cv::resize; only the 8-bit kernels exist here, and an
+      // F32 frame (e.g. a flow field) must not be silently reinterpreted as bytes
+      STB_FATAL("Resize (B200): only U8 frames with 1, 3 or 4 channels are implemented");
+    }
+    FrameInfo info(target_height, target_width, ch, frame->type);
     std::vector<Frame*> output_frames = new_frames(device_, info, input_count);
     src_.resize(input_count);
     dst_.resize(input_count);
@@ -145,6 +151,7 @@ REGISTER_OP(Resize).frame_input("frame").frame_output("frame");
 REGISTER_KERNEL(Resize, ResizeKernelGPU).device(DeviceType::GPU).batch().num_devices(1);
 
 // test harness hook (compat build only): run the kernel with serialized args
+#ifdef STB_COMPAT_SHIM
 extern "C" __attribute__((visibility("default"))) int stb_shim_resize(const uint8_t* h_frames, int n, int w, int h, int c,
                                                                       const uint8_t* args, int args_len, uint8_t* h_out,
                                                                       int out_capacity, int* out_w, int* out_h, int device_id) {
@@ -178,4 +185,5 @@ extern "C" __attribute__((visibility("default"))) int stb_shim_resize(const uint
   for (Frame* f : in) delete f;
   return rc;
 }
+#endif  // STB_COMPAT_SHIM
 }  // namespace scanner

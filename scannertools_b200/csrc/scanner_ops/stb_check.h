@@ -15,3 +15,11 @@
       abort();                                                                             \
     }                                                                                      \
   } while (0)
+
+// unrecoverable input (the reference uses glog LOG(FATAL), image_decoder_kernel_cpu.cpp:28): report and
+// abort the worker -- never reinterpret a frame of the wrong type
+#define STB_FATAL(msg)                                                              \
+  do {                                                                              \
+    fprintf(stderr, "scannertools_b200: %s (%s:%d)\n", (msg), __FILE__, __LINE__);  \
+    abort();                                                                        \
+  } while (0)

@@ -21,6 +21,8 @@ from . import _lib
 
 HIST_BINS = 16       # histogram_kernel_cpu.cpp:8
 FLOW_HIST_BINS = 64  # flow_histogram_kernel_cpu.cpp:9
+# names of resize_kernel.cpp:9-20's table without a kernel here
+RESIZE_TABLE_UNIMPLEMENTED = ('INTER_CUBIC', 'INTER_LANCZOS4', 'INTER_MAX', 'WARP_FILL_OUTLIERS', 'WARP_INVERSE_MAP')
 
 
 def _torch():
@@ -196,7 +198,11 @@ def resize(frames, width=0, height=0, min=False, preserve_aspect=False, interpol
     lib = _lib.load()
     interp = lib.stb_resize_interp_code((interpolation or '').encode())
     if interp < 0:
-        raise NotImplementedError('Resize: INTER_LINEAR, INTER_NEAREST and INTER_AREA are implemented (got %r)' % (interpolation,))
+        # resize_kernel.cpp:31-35: names outside the reference's INTERP_TYPES table silently mean INTER_LINEAR
+        # (mirrored, like ResizeKernelGPU does); names INSIDE the table that are not implemented here raise
+        if interpolation in RESIZE_TABLE_UNIMPLEMENTED:
+            raise NotImplementedError('Resize: INTER_LINEAR, INTER_NEAREST and INTER_AREA are implemented (got %r)' % (interpolation,))
+        interp = lib.stb_resize_interp_code(b'INTER_LINEAR')
     if isinstance(frames, torch.Tensor) and frames.dim() == 3:
         frames = frames.unsqueeze(0)
     lst = [frames[i] for i in range(frames.shape[0])] if isinstance(frames, torch.Tensor) else list(frames)
@@ -289,6 +295,9 @@ class OpticalFlow:
             raise ValueError('frame size %dx%d does not match the kernel FrameInfo %dx%d' % (W, H, self.width, self.height))
         if len(lst) - 1 > self.max_batch:
             raise ValueError('batch of %d pairs exceeds max_batch=%d' % (len(lst) - 1, self.max_batch))
+        for f in lst:
+            if f.device != self.device:     # the handle's workspace lives on self.device (check_frame(device_, ...))
+                raise ValueError('frame on %s, but this OpticalFlow kernel was created on %s' % (f.device, self.device))
 
     def execute(self, frames, out=None, stream=None, gray=False):
         torch = _torch()
@@ -301,6 +310,9 @@ class OpticalFlow:
             out = torch.empty((max(n, 0), H, W, 2), dtype=torch.float32, device=self.device)
         else:
             _require_cuda(out, torch.float32, 'out')
+            if tuple(out.shape) != (max(n, 0), H, W, 2) or out.device != self.device:
+                raise ValueError('out must be float32 [%d, %d, %d, 2] on %s, got %s on %s'
+                                 % (max(n, 0), H, W, self.device, tuple(out.shape), out.device))
         if n == 0:
             return out
         with torch.cuda.device(self.device):
@@ -386,20 +398,27 @@ class Pipe:
                                                C.c_void_p(S.ctypes.data) if scores else None), self._lib)
         return hist, S
 
-    def flow_async(self, frames, hist_out):
+    def flow_async(self, frames, hist_out, flow_out=None):
         """Asynchronous OpticalFlow -> FlowHistogram: enqueues the call and returns a ticket for
         `wait`.  `frames` (host, ideally pinned) and `hist_out` (int32 [n,2,64] numpy or pinned
         tensor) must stay untouched until then.  Two calls may be in flight: submit call i+1, then
-        wait for call i, and the uploads of one call hide behind the kernels of the other."""
+        wait for call i, and the uploads of one call hide behind the kernels of the other.
+        flow_out (float32 [n,H,W,2] host buffer, ideally pinned) additionally returns the flow frames."""
         torch = _torch()
         ptr, shape = self._host_ptr(frames)
         n = shape[0] - 1
         optr, oshape = self._host_ptr(hist_out)
         if int(np.prod(oshape)) != n * 2 * FLOW_HIST_BINS:
             raise ValueError('hist_out must hold n x 2 x 64 int32')
+        flp = None
+        if flow_out is not None:
+            fptr, fshape = self._host_ptr(flow_out)
+            if tuple(fshape) != (n, self.height, self.width, 2) or getattr(flow_out, 'dtype', None) not in (np.float32, torch.float32):
+                raise ValueError('flow_out must be float32 [n, H, W, 2]')
+            flp = C.c_void_p(fptr)
         t = C.c_int(-1)
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.stb_pipe_flow_async(self._p, C.c_void_p(ptr), n, None, C.c_void_p(optr), C.byref(t)), self._lib)
+            _lib.check(self._lib.stb_pipe_flow_async(self._p, C.c_void_p(ptr), n, flp, C.c_void_p(optr), C.byref(t)), self._lib)
         return t.value
 
     def wait(self, ticket):

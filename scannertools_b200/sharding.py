@@ -39,16 +39,29 @@ def gather_frame_outputs(local, n_frames, rank, world, group=None):
     return out
 
 
-def sharded_shot_detection(frames_of_rank, n_frames, rank, world, histogram_fn, scores_fn, prev_hist=None):
+def sharded_shot_detection(frames_of_rank, n_frames, rank, world, histogram_fn, scores_fn, prev_hist=None, halo_frame=None):
     """Shot detection over a frame-range-sharded clip.
 
     frames_of_rank : this rank's frames [f0, f1)
     histogram_fn   : frames -> int32 [m, 3, 16]     (ops.histogram on the GPU path)
     scores_fn      : (hist, prev_hist or None) -> int32 [m]   (ops.shot_scores)
-    prev_hist      : histogram of frame f0-1 (from the neighbouring rank); None on rank 0
+    halo_frame     : frame f0-1 as a one-frame batch [1, H, W, 3] (the previous shard's last frame, which
+                     this rank reads itself -- nothing is exchanged between GPUs); its histogram is
+                     computed here.  Alternatively pass that histogram as prev_hist.
+    A shard that does not start the stream (f0 > 0) MUST get one of the two: without it the first
+    score of the shard would silently be 0 and a cut on the shard seam would be lost.
     Returns (boundaries, scores[n_frames]) on every rank: the +-500-frame window test spans shard
     boundaries, so it runs once over the concatenated scores (shot_detection.py:22-26)."""
     from . import shot_detection
+    f0, f1 = frame_range(n_frames, rank, world)
+    if f1 - f0 != len(frames_of_rank):
+        raise ValueError('rank %d owns frames [%d, %d) but got %d frames' % (rank, f0, f1, len(frames_of_rank)))
+    if f0 > 0 and f1 > f0 and prev_hist is None:
+        if halo_frame is None:
+            raise ValueError('shard [%d, %d) does not start the stream: pass halo_frame (frame %d) or prev_hist' % (f0, f1, f0 - 1))
+        prev_hist = histogram_fn(halo_frame)[0]
+    if f0 == 0:
+        prev_hist = None         # stream start: diffs[0] = 0 (shot_detection.py:18)
     hist = histogram_fn(frames_of_rank)
     scores = scores_fn(hist, prev_hist)
     all_scores = gather_frame_outputs(scores, n_frames, rank, world)

@@ -28,12 +28,19 @@ def texture_rgb(seed, h, w, sigma=2.5):
     return np.stack(chans, axis=-1)
 
 
-def textured_clip(seed, n_frames, h, w, sigma=2.5, max_shift=4.0, n_blobs=3):
+def textured_clip(seed, n_frames, h, w, sigma=2.5, max_shift=4.0, n_blobs=3, t0=0, total=None):
     """n_frames x h x w x 3 uint8.  Background translates sub-pixel (bilinear warp) by a
-    seeded velocity; n_blobs textured discs move independently on top."""
+    seeded velocity; n_blobs textured discs move independently on top.
+
+    t0 / total: frames [t0, t0 + n_frames) of the clip of `total` frames with this seed -- every
+    frame depends only on (seed, total, its own index), so a frame-range shard of a long clip is
+    generated without generating the rest (textured_clip(s, n, h, w, t0=a, total=T) ==
+    textured_clip(s, T, h, w)[a:a + n])."""
     import cv2
     rng = np.random.default_rng(seed)
-    pad = int(np.ceil(max_shift * n_frames)) + 8
+    if total is None:
+        total = t0 + n_frames
+    pad = int(np.ceil(max_shift * total)) + 8
     pad = min(pad, 64 + 8)
     big = texture_rgb(seed, h + 2 * pad, w + 2 * pad, sigma)
     vel = rng.uniform(-max_shift, max_shift, size=2).astype(np.float64)
@@ -48,7 +55,8 @@ def textured_clip(seed, n_frames, h, w, sigma=2.5, max_shift=4.0, n_blobs=3):
         bv = rng.uniform(-max_shift, max_shift, size=2)
         blobs.append((r, tex, alpha, pos, bv))
     out = np.empty((n_frames, h, w, 3), np.uint8)
-    for t in range(n_frames):
+    for ti in range(n_frames):
+        t = t0 + ti
         # wrap the accumulated shift into the padding so long clips stay in range
         sx = ((vel[0] * t + (pad - 8)) % (2 * (pad - 8))) - (pad - 8)
         sy = ((vel[1] * t + (pad - 8)) % (2 * (pad - 8))) - (pad - 8)
@@ -65,6 +73,32 @@ def textured_clip(seed, n_frames, h, w, sigma=2.5, max_shift=4.0, n_blobs=3):
             ts = tex[y0 - (cy - r):y1 - (cy - r), x0 - (cx - r):x1 - (cx - r)]
             al = alpha[y0 - (cy - r):y1 - (cy - r), x0 - (cx - r):x1 - (cx - r)]
             frame[y0:y1, x0:x1] = frame[y0:y1, x0:x1] * (1 - al) + ts * al
+        out[ti] = np.clip(frame * 255.0 + 0.5, 0, 255).astype(np.uint8)
+    return out
+
+
+def warped_clip(seed, n_frames, h, w, sigma=2.5):
+    """n_frames x h x w x 3 uint8: one band-limited texture under a smooth global motion -- sub-pixel
+    translation plus a small rotation and zoom about a seeded centre -- so the flow field covers a
+    continuous range of magnitudes and directions and nothing moves exactly along an axis or by an
+    integer vector.  (textured_clip's blobs move by integer vectors, i.e. exactly ON the 0/45/90 degree
+    bin edges of the FlowHistogram angle axis: fine for flow parity, degenerate for per-bin counts.)"""
+    import cv2
+    rng = np.random.default_rng([seed, 77])
+    pad = 48
+    big = texture_rgb(seed + 4000, h + 2 * pad, w + 2 * pad, sigma)
+    vel = rng.uniform(1.1, 2.9, size=2) * rng.choice([-1.0, 1.0], size=2)
+    theta = float(rng.uniform(0.6, 1.2)) * 3.0 / max(h, w) * float(rng.choice([-1.0, 1.0]))   # ~ +-3 px at the far corner
+    zoom = 1.0 + float(rng.uniform(0.3, 0.9)) * 2.0 / max(h, w)
+    cx, cy = w * float(rng.uniform(0.35, 0.65)), h * float(rng.uniform(0.35, 0.65))
+    out = np.empty((n_frames, h, w, 3), np.uint8)
+    for t in range(n_frames):
+        a, s = theta * t, zoom ** t
+        c, sn = np.cos(a) * s, np.sin(a) * s
+        # destination (x, y) -> source: rotate/zoom about (cx, cy), translate, shift into the padded texture
+        Mw = np.array([[c, -sn, cx - c * cx + sn * cy + pad - vel[0] * t],
+                       [sn, c, cy - sn * cx - c * cy + pad - vel[1] * t]], np.float64)
+        frame = cv2.warpAffine(big, Mw, (w, h), flags=cv2.INTER_LINEAR | cv2.WARP_INVERSE_MAP)
         out[t] = np.clip(frame * 255.0 + 0.5, 0, 255).astype(np.uint8)
     return out
 
@@ -94,6 +128,27 @@ def cut_clip(seed, n_frames, h, w, n_cuts=7, noise=3):
             nz = rng.integers(-noise, noise + 1, size=(h, w, 3)).astype(np.float32)
             out[t] = np.clip(base + nz, 0, 255).astype(np.uint8)
     return out, cuts
+
+
+def cut_clip_range(seed, n_total, h, w, t0, t1, cuts, noise=3):
+    """Frames [t0, t1) of an n_total-frame clip with hard cuts at the given frame indices (frame c
+    is the first frame of a new shot), generated without the rest of the clip: shot s has a base
+    image seeded by (seed, s) and every frame its own noise seeded by (seed, t).  Used for
+    frame-range-sharded shot detection, where `cuts` may be planted exactly on shard seams."""
+    import cv2
+    bounds = [0] + sorted(int(c) for c in cuts) + [n_total]
+    out = np.empty((max(t1 - t0, 0), h, w, 3), np.uint8)
+    bases = {}
+    for t in range(t0, t1):
+        s = max(i for i in range(len(bounds) - 1) if bounds[i] <= t)
+        if s not in bases:
+            rs = np.random.default_rng([seed, 1, s])
+            small = rs.integers(0, 256, size=(9, 16, 3), dtype=np.uint8)
+            base = cv2.resize(small, (w, h), interpolation=cv2.INTER_CUBIC).astype(np.float32)
+            bases[s] = base * float(rs.uniform(0.4, 1.0))
+        nz = np.random.default_rng([seed, 2, t]).integers(-noise, noise + 1, size=(h, w, 3), dtype=np.int8)
+        out[t - t0] = np.clip(bases[s] + nz, 0, 255).astype(np.uint8)
+    return out
 
 
 def noise_clip(seed, n_frames, h, w):

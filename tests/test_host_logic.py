@@ -65,3 +65,82 @@ def test_numa_binding_helpers(tmp_path):
     before = os.sched_getaffinity(0)
     assert sharding.bind_to_gpu_numa_node(0, sysfs=str(tmp_path)) is None
     assert os.sched_getaffinity(0) == before
+
+
+def test_scanner_registration_shim_registers_shot_boundaries(golden):
+    """scannertools_b200.scanner_register mirrors `@scannerpy.register_python_op(name='ShotBoundaries',
+    batch=BOUNDARY_BATCH)` (shot_detection.py:11) and the imgproc library registration
+    (imgproc/__init__.py:1-3).  scannerpy is not in this image: a recording stub stands in."""
+    import importlib
+    import sys
+    import types as pytypes
+    calls = {}
+    sp = pytypes.ModuleType('scannerpy')
+
+    def register_python_op(**kwargs):
+        def deco(fn):
+            calls['op'] = (kwargs, fn)
+            return fn
+        return deco
+    sp.register_python_op = register_python_op
+    st = pytypes.ModuleType('scannerpy.types')
+    st.Histogram = object
+    op = pytypes.ModuleType('scannerpy.op')
+    op.register_module = lambda so, proto=None: calls.setdefault('module', (so, proto))
+    sp.op = op
+    saved = {k: sys.modules.get(k) for k in ('scannerpy', 'scannerpy.types', 'scannerpy.op')}
+    sys.modules.update({'scannerpy': sp, 'scannerpy.types': st, 'scannerpy.op': op})
+    try:
+        sys.modules.pop('scannertools_b200.scanner_register', None)
+        mod = importlib.import_module('scannertools_b200.scanner_register')
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        sys.modules.pop('scannertools_b200.scanner_register', None)
+    kwargs, fn = calls['op']
+    assert kwargs == {'name': 'ShotBoundaries', 'batch': 10000000}
+    assert calls['module'][0].endswith('libscannertools_imgproc.so')
+    assert mod.WINDOW_SIZE == 500
+    g = golden('shot_c1.npz')
+    elements = [types.histograms(types.histogram_bytes(h)) for h in g['hists'].reshape(-1, 3, 16)]
+    rows = fn(None, elements)
+    assert rows[0] == list(g['boundaries']) and all(r is None for r in rows[1:])
+
+
+def test_scanner_registration_needs_scannerpy():
+    import importlib
+    import sys
+    import pytest
+    if 'scannerpy' in sys.modules:
+        pytest.skip('a scannerpy (stub) is loaded')
+    sys.modules.pop('scannertools_b200.scanner_register', None)
+    with pytest.raises(ImportError):
+        importlib.import_module('scannertools_b200.scanner_register')
+
+
+def test_synthetic_clips_are_shardable_by_frame_range():
+    from scannertools_b200 import synth
+    whole = synth.textured_clip(5, 40, 45, 80)
+    part = synth.textured_clip(5, 7, 45, 80, t0=20, total=40)
+    assert np.array_equal(whole[20:27], part)
+    cuts = [9, 16, 20]
+    a = synth.cut_clip_range(3, 32, 36, 64, 0, 32, cuts)
+    b = synth.cut_clip_range(3, 32, 36, 64, 15, 21, cuts)
+    assert np.array_equal(a[15:21], b)
+    # a cut changes the shot's base image: large frame difference exactly at the cut
+    d = np.abs(a[1:].astype(np.int32) - a[:-1]).mean(axis=(1, 2, 3))
+    assert set(np.nonzero(d > 8)[0] + 1) == set(cuts)
+
+
+def test_sharded_shot_detection_requires_the_halo():
+    import pytest
+    fr = np.zeros((4, 2, 2, 3), np.uint8)
+    hist = lambda f: np.zeros((len(f), 3, 16), np.int32)
+    sc = lambda h, p: np.zeros(len(h), np.int32)
+    with pytest.raises(ValueError):      # rank 1 of 2 without halo frame / prev_hist: a seam cut would be lost silently
+        sharding.sharded_shot_detection(fr, 8, 1, 2, hist, sc)
+    with pytest.raises(ValueError):      # wrong number of frames for the shard
+        sharding.sharded_shot_detection(fr[:3], 8, 0, 2, hist, sc)

@@ -32,15 +32,26 @@ def _pair_feature(f0, f1):
     return np.array([int(f0.astype(np.int64).sum()) - int(f1.astype(np.int64).sum())], np.int64)
 
 
+def _cuts(n_frames, world):
+    # planted cuts, one of them EXACTLY on the shard seam (first frame of rank 1's range)
+    seam = sharding.frame_range(n_frames, 1, world)[0]
+    return sorted({40, 97, seam, n_frames - 30})
+
+
 def _worker(rank, world, port, n_frames, out_dir):
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
-    clip, cuts = synth.cut_clip(17, n_frames, 18, 32, n_cuts=4)
     f0, f1 = sharding.frame_range(n_frames, rank, world)
-    prev = _np_hist(clip[f0 - 1:f0])[0] if f0 > 0 else None      # one-histogram halo from the neighbour's range
-    bounds, scores = sharding.sharded_shot_detection(clip[f0:f1], n_frames, rank, world, _np_hist, _np_scores, prev)
+    cuts = _cuts(n_frames, world)
+    # each rank generates ONLY its own frames (+ the one halo frame before its range) from the seed
+    a0 = max(f0 - 1, 0)
+    mine_fr = synth.cut_clip_range(17, n_frames, 18, 32, a0, f1, cuts)
+    halo = mine_fr[0:1] if f0 > 0 else None
+    bounds, scores = sharding.sharded_shot_detection(mine_fr[f0 - a0:], n_frames, rank, world, _np_hist, _np_scores,
+                                                     halo_frame=halo)
+    clip = synth.cut_clip_range(17, n_frames, 18, 32, 0, n_frames, cuts)
     (p0, p1), (a, b) = sharding.pair_range(n_frames, rank, world)
     mine = np.stack([_pair_feature(clip[i], clip[i + 1]) for i in range(p0, p1)]) if p1 > p0 else np.zeros((0, 1), np.int64)
     assert (a, b) == ((p0, p1 + 1) if p1 > p0 else (p0, p0))     # one halo frame
@@ -61,7 +72,9 @@ def _free_port():
 def test_two_rank_frame_range_sharding_matches_single_rank(tmp_path):
     n = 301   # odd: uneven shards
     mp.spawn(_worker, args=(2, _free_port(), n, str(tmp_path)), nprocs=2, join=True)
-    clip, cuts = synth.cut_clip(17, n, 18, 32, n_cuts=4)
+    cuts = _cuts(n, 2)
+    clip = synth.cut_clip_range(17, n, 18, 32, 0, n, cuts)
+    assert sharding.frame_range(n, 1, 2)[0] in cuts
     ref_scores = _np_scores(_np_hist(clip), None)
     ref_bounds = shot_detection.boundaries_from_scores(ref_scores)
     ref_pairs = np.stack([_pair_feature(clip[i], clip[i + 1]) for i in range(n - 1)])
