@@ -73,18 +73,48 @@ def ncu_traffic():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region: the sampler is started
-    before the warm-up (nvidia-smi takes a few hundred ms to start) and only rows whose timestamp
-    falls inside [t0, t1] of the timed region are kept."""
+    """SM clock, power and clock-event (throttle) reasons sampled DURING the timed region by a thread
+    polling NVML every ~5 ms (the main thread sits in C calls that release the GIL); only samples
+    taken inside [t0, t1] of the timed region are kept.  Falls back to parsing `nvidia-smi -lms` when
+    NVML cannot be loaded."""
     Q = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, pci_bus_id=None):
         self.idx = gpu_index
-        self.rows = []
+        self.pci = pci_bus_id
+        self.samples = []      # (time, sm_mhz, max_mhz, power_w, reasons-set)
         self.proc = None
+        self.thread = None
+        self.stop_flag = False
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(self.pci.encode() if hasattr(self.pci, 'encode') else self.pci) \
+                if self.pci else pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = {'hw_slowdown': pynvml.nvmlClocksEventReasonHwSlowdown, 'hw_thermal_slowdown': pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                     'sw_thermal_slowdown': pynvml.nvmlClocksEventReasonSwThermalSlowdown, 'sw_power_cap': pynvml.nvmlClocksEventReasonSwPowerCap,
+                     'hw_power_brake': pynvml.nvmlClocksEventReasonHwPowerBrakeSlowdown}
+
+            def poll():
+                while not self.stop_flag:
+                    try:
+                        t = time.time()
+                        sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                        mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        self.samples.append((t, sm, mx, pw, {n for n, bit in names.items() if mask & bit}))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
                                           '--format=csv,noheader,nounits', '-lms', '20'],
@@ -95,41 +125,47 @@ class ClockSampler:
             self.proc = None
 
     def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def stop(self, t0=None, t1=None):
-        if not self.proc:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
-        time.sleep(0.05)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         import datetime
-        for seen, r in self.rows:
-            f = [x.strip() for x in r.split(',')]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.strip().split(',')]
             if len(f) < 9:
                 continue
-            ts = seen
+            ts = time.time()
             try:
                 ts = datetime.datetime.strptime(f[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
             except ValueError:
                 pass
-            if t0 is not None and not (t0 - 0.02 <= ts <= t1 + 0.02):
-                continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                self.samples.append((ts, float(f[1]), float(f[2]), float(f[3]),
+                                     {n for n, v in zip(names, f[5:9]) if v.lower().startswith('active')}))
             except ValueError:
                 continue
-            for nme, v in zip(names, f[5:9]):
-                if v.lower().startswith('active'):
-                    reasons.add(nme)
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+    def stop(self, t0=None, t1=None):
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=1)
+            source = 'nvml'
+        elif self.proc:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+            source = 'nvidia-smi'
+        else:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        rows = [r for r in self.samples if t0 is None or (t0 - 0.02 <= r[0] <= t1 + 0.02)]
+        reasons = set()
+        for r in rows:
+            reasons |= r[4]
+        return {'sm_mhz': float(np.median([r[1] for r in rows])) if rows else None,
+                'sm_min_mhz': min(r[1] for r in rows) if rows else None,
+                'sm_max_mhz': max(r[2] for r in rows) if rows else None,
+                'power_w_max': max(r[3] for r in rows) if rows else None, 'samples': len(rows), 'reasons': sorted(reasons),
+                'source': source}
 
 
 # ------------------------------------------------------------------------------ reference arm
@@ -295,7 +331,8 @@ def run_ours(args):
             ot = _lib.ptr_table(flow_ptrs[b0:b0 + B])
             _lib.check(lib.stb_farneback_run_hist(of._h, ft, B, ot, C.c_void_p(d_fh[b0].data_ptr()), sp), lib)
 
-    sampler = ClockSampler(local)
+    pr = torch.cuda.get_device_properties(local)
+    sampler = ClockSampler(local, '%08x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id))
     if rank == 0:
         sampler.start()
     for _ in range(args.warmup):

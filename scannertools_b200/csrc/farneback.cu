@@ -269,6 +269,130 @@ pyr_pow2_kernel(const uint8_t* __restrict__ gray, float* __restrict__ I, int W, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Levels 1..3 in TWO launches when every level is an exact power-of-two size and W % 32 == 0 (1080p,
+// 720p, 640x480, 4K): the same merged-tap separable FIRs as pyr_pow2_kernel, evaluated in the same
+// fmaf order (bit-identical I_k), but
+//   * pyr_h_kernel reads the gray plane ONCE for all three levels: a thread owns 32 source pixels
+//     of one row (+ 8 either side), converts its 48 bytes to float once, and emits the horizontal
+//     FIR of that row at the 16 / 8 / 4 output columns of levels 1 / 2 / 3 (taps are kernel
+//     parameters, i.e. constant-bank FFMA operands) into a narrow intermediate Hx_K [H][w_K];
+//   * pyr_v_kernel runs the three vertical FIRs (4 outputs per thread, 16-byte loads) over it.
+// pyr_pow2_kernel re-did the horizontal FIR per 8/16-row tile, per level, with one LDS.U8 + I2F per
+// tap: 144 us per 17 1080p frames; these two: 72 us.
+// ---------------------------------------------------------------------------------------------
+struct PyrTaps3 { float c1[4], c2[10], c3[20]; };
+
+__device__ __forceinline__ void unpack4(unsigned wd, float* f) {
+  f[0] = (float)(wd & 0xffu); f[1] = (float)((wd >> 8) & 0xffu); f[2] = (float)((wd >> 16) & 0xffu); f[3] = (float)(wd >> 24);
+}
+
+__global__ void __launch_bounds__(128)
+pyr_h_kernel(const uint8_t* __restrict__ gray, float* __restrict__ Hx, int W, int H, PyrTaps3 tp, int nlev, int frame0) {
+  const int nseg = W >> 5;
+  const int item = blockIdx.x * 128 + threadIdx.x;
+  if (item >= nseg * H) return;
+  const int y = item / nseg, seg = item - y * nseg;
+  const int frame = frame0 + blockIdx.y;
+  const uint8_t* row = gray + ((size_t)frame * H + y) * W;
+  const int x0 = seg * 32;
+  float v[48];                      // v[j] = gray[x0 - 8 + j] with REFLECT_101 at the row ends
+  if (seg > 0 && seg < nseg - 1) {
+    const uint2 a = __ldg(reinterpret_cast<const uint2*>(row + x0 - 8));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(row + x0));
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(row + x0 + 16));
+    const uint2 d = __ldg(reinterpret_cast<const uint2*>(row + x0 + 32));
+    unpack4(a.x, v); unpack4(a.y, v + 4);
+    unpack4(b.x, v + 8); unpack4(b.y, v + 12); unpack4(b.z, v + 16); unpack4(b.w, v + 20);
+    unpack4(c.x, v + 24); unpack4(c.y, v + 28); unpack4(c.z, v + 32); unpack4(c.w, v + 36);
+    unpack4(d.x, v + 40); unpack4(d.y, v + 44);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 48; ++j) v[j] = (float)__ldg(row + reflect101(x0 - 8 + j, W));
+  }
+  // frame-major intermediate: [frame][level-1 rows | level-2 rows | level-3 rows]
+  const int w1 = W >> 1, w2 = W >> 2, w3 = W >> 3;
+  float* base = Hx + (size_t)frame * H * (w1 + w2 + w3);
+  {   // level 1: S = 2, 4 taps, first tap of output o at source 2o - 1
+    float* o = base + (size_t)y * w1 + seg * 16;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float r[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float a = 0.f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) a = fmaf(tp.c1[t], v[8 + 2 * (4 * q + i) - 1 + t], a);
+        r[i] = a;
+      }
+      *reinterpret_cast<float4*>(o + 4 * q) = make_float4(r[0], r[1], r[2], r[3]);
+    }
+  }
+  if (nlev >= 2) {   // level 2: S = 4, 10 taps, first tap at 4o - 3
+    float* o = base + (size_t)H * w1 + (size_t)y * w2 + seg * 8;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float r[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float a = 0.f;
+#pragma unroll
+        for (int t = 0; t < 10; ++t) a = fmaf(tp.c2[t], v[8 + 4 * (4 * q + i) - 3 + t], a);
+        r[i] = a;
+      }
+      *reinterpret_cast<float4*>(o + 4 * q) = make_float4(r[0], r[1], r[2], r[3]);
+    }
+  }
+  if (nlev >= 3) {   // level 3: S = 8, 20 taps, first tap at 8o - 6
+    float* o = base + (size_t)H * (w1 + w2) + (size_t)y * w3 + seg * 4;
+    float r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float a = 0.f;
+#pragma unroll
+      for (int t = 0; t < 20; ++t) a = fmaf(tp.c3[t], v[8 + 8 * i - 6 + t], a);
+      r[i] = a;
+    }
+    *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+// vertical FIRs: one thread = 4 adjacent outputs of one level; blockIdx.x walks the quads of
+// level 1, then level 2, then level 3.  I_k of frame f lives at I + f * stride_f + off_k.
+template <int K>
+__device__ __forceinline__ void pyr_v_quad(const float* __restrict__ hx, float* __restrict__ out, int wK, int H, int q,
+                                           const float* taps) {
+  constexpr int S = 1 << K;
+  constexpr int RAD = (K == 1) ? 1 : (K == 2 ? 4 : 9);
+  constexpr int NT = 2 * RAD + 2;
+  const int qpr = wK >> 2;                      // quads per row
+  const int oy = q / qpr, ox = (q - oy * qpr) * 4;
+  const int r_lo = S * oy + S / 2 - 1 - RAD;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const float4 h = __ldg(reinterpret_cast<const float4*>(hx + (size_t)reflect101(r_lo + t, H) * wK + ox));
+    a0 = fmaf(taps[t], h.x, a0); a1 = fmaf(taps[t], h.y, a1); a2 = fmaf(taps[t], h.z, a2); a3 = fmaf(taps[t], h.w, a3);
+  }
+  *reinterpret_cast<float4*>(out + (size_t)oy * wK + ox) = make_float4(a0, a1, a2, a3);
+}
+
+__global__ void __launch_bounds__(128)
+pyr_v_kernel(const float* __restrict__ Hx, float* __restrict__ I, int W, int H, PyrTaps3 tp, int nlev, size_t frame_stride,
+             int frame0) {
+  const int w1 = W >> 1, w2 = W >> 2, w3 = W >> 3;
+  const int n1 = (w1 >> 2) * (H >> 1), n2 = nlev >= 2 ? (w2 >> 2) * (H >> 2) : 0, n3 = nlev >= 3 ? (w3 >> 2) * (H >> 3) : 0;
+  const int frame = frame0 + blockIdx.y;
+  const float* hx = Hx + (size_t)frame * H * (w1 + w2 + w3);
+  float* out = I + (size_t)frame * frame_stride;
+  int q = blockIdx.x * 128 + threadIdx.x;
+  if (q < n1) { pyr_v_quad<1>(hx, out, w1, H, q, tp.c1); return; }
+  q -= n1;
+  if (q < n2) { pyr_v_quad<2>(hx + (size_t)H * w1, out + (size_t)w1 * (H >> 1), w2, H, q, tp.c2); return; }
+  q -= n2;
+  if (q < n3) pyr_v_quad<3>(hx + (size_t)H * (w1 + w2), out + (size_t)w1 * (H >> 1) + (size_t)w2 * (H >> 2), w3, H, q, tp.c3);
+}
+
+// ---------------------------------------------------------------------------------------------
 // level 0 of the pyramid: 3x3 separable Gaussian (taps t0,t1,t2; REFLECT_101), no resize.
 // Each thread produces a 4 (x) by 4 (y) patch: 6 source rows x (one aligned 4-byte load + the
 // two neighbouring bytes), horizontal blur per row, vertical combine, float4 stores.
@@ -362,14 +486,14 @@ constexpr int kPeRows = 8 + 2 * kPolyN;       // 18 input rows per vertical item
 // Horizontal pass: item = (row, 4 adjacent columns): 16-byte shared loads of a 20-float window
 // per component, 11-tap sums in registers, float4 stores of the 5 output planes.
 __global__ void __launch_bounds__(kPeThreads, 4)
-polyexp_kernel(const float* __restrict__ I, float* __restrict__ R, int w, int h, PolyConsts c, int frame0) {
+polyexp_kernel(const float* __restrict__ I, size_t i_stride, float* __restrict__ R, int w, int h, PolyConsts c, int frame0) {
   // (A prefetch-ahead of the I tile, as in updmat_init_kernel, measured neutral here: the reads are
   // 1/6 of this kernel's traffic.)
   __shared__ __align__(16) float V[3][kPeTH][kPeStride];
   const int tid = threadIdx.x;
   const int frame = frame0 + blockIdx.z;
   const int n = w * h;
-  const float* src = I + (size_t)frame * n;
+  const float* src = I + (size_t)frame * i_stride;
   float* dst = R + (size_t)frame * 5 * n;
   const int ox0 = blockIdx.x * kPeTW, oy0 = blockIdx.y * kPeTH;
 
@@ -503,12 +627,12 @@ __device__ __forceinline__ void polyexp_column(const float* __restrict__ src, in
 }
 
 __global__ void __launch_bounds__(256)
-polyexp_generic_kernel(const float* __restrict__ I, float* __restrict__ R, int w, int h, PolyConsts c, int n, int frame0) {
+polyexp_generic_kernel(const float* __restrict__ I, size_t i_stride, float* __restrict__ R, int w, int h, PolyConsts c, int n, int frame0) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= w || y >= h) return;
   const int frame = frame0 + blockIdx.z;
   const int npx = w * h;
-  const float* src = I + (size_t)frame * npx;
+  const float* src = I + (size_t)frame * i_stride;
   float* dst = R + (size_t)frame * 5 * npx + y * w + x;
   float c0, c1, c2;
   polyexp_column(src, w, h, x, y, n, c, c0, c1, c2);
@@ -1290,6 +1414,9 @@ struct stb_farneback {
   MergedTaps merged[kMaxScales];
   int pow2[kMaxScales];
   int chunk[kMaxScales];
+  int fast_pyr;          // levels 1.. from one horizontal + one vertical launch (pyr_h_kernel / pyr_v_kernel)
+  PyrTaps3 taps3;
+  int init_prefetch_waves;   // updmat_init_kernel's prefetch distance in resident waves
   // device workspace
   uint8_t* gray;    // [F][H*W]
   float* I;         // [F][N_k]      (N_0 sized)
@@ -1556,6 +1683,17 @@ int stb_farneback_create(int width, int height, int max_pairs, const stb_farneba
     int c = kMaxPtrBatch;
     h->chunk[k] = c;
   }
+  {
+    // two-launch pyramid for levels >= 1: every level an exact power-of-two size, 32-pixel segments
+    bool ok = h->nscales >= 2 && (width % 32) == 0 && !getenv("STB_NO_FAST_PYR");
+    for (int k = 1; k < h->nscales; ++k) ok = ok && h->pow2[k];
+    h->fast_pyr = ok ? 1 : 0;
+    for (int t = 0; t < 4; ++t) h->taps3.c1[t] = h->nscales > 1 ? h->merged[1].c[t] : 0.f;
+    for (int t = 0; t < 10; ++t) h->taps3.c2[t] = h->nscales > 2 ? h->merged[2].c[t] : 0.f;
+    for (int t = 0; t < 20; ++t) h->taps3.c3[t] = h->nscales > 3 ? h->merged[3].c[t] : 0.f;
+    h->init_prefetch_waves = 2;
+    if (const char* env = getenv("STB_INIT_PREFETCH_WAVES")) h->init_prefetch_waves = atoi(env);
+  }
   if (const char* env = getenv("STB_CHUNKS")) {   // experiment knob: "c0,c1,c2,c3" pairs per launch per level
     int k = 0;
     for (const char* pch = env; *pch && k < h->nscales; ++k) {
@@ -1699,9 +1837,30 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
   const int m = h->prm.win_size / 2;
   const size_t it_smem = iter_smem_bytes(m);
   int fl_cur = 0;  // h->flow[fl_cur] receives this level's flow (levels >= 1)
+  // Levels >= 1 of all n + 1 frames from two launches (the intermediate lives in the R buffer, which is
+  // not written before the first polynomial expansion; I_1.. are packed into the I buffer, which level 0
+  // only overwrites after they have been consumed).  Needs the batch in one chunk at every level.
+  bool fastpyr = h->fast_pyr != 0;
+  for (int k = 0; k < h->nscales; ++k) fastpyr = fastpyr && n <= h->chunk[k];
+  const size_t N0 = (size_t)h->W * h->H;
+  if (fastpyr) {
+    const int nlev = h->nscales - 1;
+    const int items = (h->W >> 5) * h->H;
+    stb_launch(pyr_h_kernel, dim3(ceil_div(items, 128), F), dim3(128), 0, s, (const uint8_t*)h->gray, h->R, h->W, h->H, h->taps3, nlev, 0);
+    STB_CHECK_LAUNCH("pyr_h_kernel");
+    int quads = 0;
+    for (int k = 1; k <= nlev; ++k) quads += (h->w[k] >> 2) * h->h[k];
+    stb_launch(pyr_v_kernel, dim3(ceil_div(quads, 128), F), dim3(128), 0, s, (const float*)h->R, h->I, h->W, h->H, h->taps3, nlev, N0, 0);
+    STB_CHECK_LAUNCH("pyr_v_kernel");
+  }
   for (int k = h->nscales - 1; k >= 0; --k) {
     const int w = h->w[k], hh = h->h[k];
     const size_t nk = (size_t)w * hh;
+    // I_k of frame f: Ik + f * i_stride
+    size_t i_off = 0;
+    if (fastpyr) for (int j = 1; j < k; ++j) i_off += (size_t)h->w[j] * h->h[j];
+    const float* Ik = h->I + i_off;
+    const size_t i_stride = (fastpyr && k >= 1) ? N0 : nk;
     const PyrParams& pp = h->pyr[k];
     const float* coarse = (k == h->nscales - 1) ? nullptr : h->flow[fl_cur ^ 1];
     const int wc = coarse ? h->w[k + 1] : 0, hc = coarse ? h->h[k + 1] : 0;
@@ -1714,7 +1873,9 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
       // frames [fa, fb) still need I_k and R_k
       const int fa = frames_done, fb = p1 + 1;
       if (fb > fa) {
-        if (k == 0) {
+        if (fastpyr && k >= 1) {
+          // already there
+        } else if (k == 0) {
           // rows of the gray plane and of I are 4/16-byte aligned iff W % 4 == 0 (bases are 256-byte aligned)
           stb_launch(pyr0_kernel, dim3(ceil_div(w, 128), ceil_div(hh, 32), fb - fa), dim3(256), 0, s,
                      (const uint8_t*)h->gray, h->I, w, hh, pp.taps[0], pp.taps[1], pp.taps[2], fa, (w % 4 == 0) ? 1 : 0);
@@ -1733,10 +1894,10 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
         }
         if (h->prm.poly_n == kPolyN)
           stb_launch(polyexp_kernel, dim3(ceil_div(w, kPeTW), ceil_div(hh, kPeTH), fb - fa), dim3(kPeThreads), 0, s,
-                     (const float*)h->I, h->R, w, hh, h->pc, fa);
+                     Ik, i_stride, h->R, w, hh, h->pc, fa);
         else
           stb_launch(polyexp_generic_kernel, dim3(ceil_div(w, 32), ceil_div(hh, 8), fb - fa), dim3(256), 0, s,
-                     (const float*)h->I, h->R, w, hh, h->pc, h->prm.poly_n, fa);
+                     Ik, i_stride, h->R, w, hh, h->pc, h->prm.poly_n, fa);
         STB_CHECK_LAUNCH("polyexp_kernel");
         frames_done = fb;
       }
@@ -1744,16 +1905,15 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
       {
         // prefetch distance: about two resident waves expressed in block rows
         const int bx = ceil_div(w, 64);
-        int ahead = h->prefetch_Ri[k] ? ceil_div(2 * 4 * num_sms(), bx) : 0;
-        if (const char* env = getenv("STB_INIT_PREFETCH_WAVES")) ahead = h->prefetch_Ri[k] ? ceil_div(atoi(env) * 4 * num_sms(), bx) : 0;
+        const int ahead = h->prefetch_Ri[k] ? ceil_div(h->init_prefetch_waves * 4 * num_sms(), bx) : 0;
         stb_launch(updmat_init_kernel, dim3(bx, ceil_div(hh, 8), np), dim3(256), 0, s, (const float*)h->R,
                    coarse, h->M[0], w, hh, wc, hc, up_sx, up_sy, (float)(1. / h->prm.pyr_scale), p0, h->tmapRi[k], ahead);
       }
       STB_CHECK_LAUNCH("updmat_init_kernel");
       if (dbg && h->dbg_pair >= p0 && h->dbg_pair < p1) {
         const int dp = h->dbg_pair;
-        if (h->dbg_I0) STB_CUDA(cudaMemcpyAsync(h->dbg_I0, h->I + (size_t)dp * nk, nk * 4, cudaMemcpyDeviceToDevice, s));
-        if (h->dbg_I1) STB_CUDA(cudaMemcpyAsync(h->dbg_I1, h->I + (size_t)(dp + 1) * nk, nk * 4, cudaMemcpyDeviceToDevice, s));
+        if (h->dbg_I0) STB_CUDA(cudaMemcpyAsync(h->dbg_I0, Ik + (size_t)dp * i_stride, nk * 4, cudaMemcpyDeviceToDevice, s));
+        if (h->dbg_I1) STB_CUDA(cudaMemcpyAsync(h->dbg_I1, Ik + (size_t)(dp + 1) * i_stride, nk * 4, cudaMemcpyDeviceToDevice, s));
         if (h->dbg_R0) STB_CUDA(cudaMemcpyAsync(h->dbg_R0, h->R + (size_t)dp * 5 * nk, nk * 20, cudaMemcpyDeviceToDevice, s));
         if (h->dbg_R1) STB_CUDA(cudaMemcpyAsync(h->dbg_R1, h->R + (size_t)(dp + 1) * 5 * nk, nk * 20, cudaMemcpyDeviceToDevice, s));
         if (h->dbg_M0) STB_CUDA(cudaMemcpyAsync(h->dbg_M0, h->M[0] + (size_t)dp * 5 * nk, nk * 20, cudaMemcpyDeviceToDevice, s));

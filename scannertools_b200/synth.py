@@ -145,7 +145,8 @@ def cut_clip_range(seed, n_total, h, w, t0, t1, cuts, noise=3):
             rs = np.random.default_rng([seed, 1, s])
             small = rs.integers(0, 256, size=(9, 16, 3), dtype=np.uint8)
             base = cv2.resize(small, (w, h), interpolation=cv2.INTER_CUBIC).astype(np.float32)
-            bases[s] = base * float(rs.uniform(0.4, 1.0))
+            # alternate dark / bright shots so every planted cut is a clear histogram change
+            bases[s] = base * float((0.45 if s % 2 == 0 else 0.9) * rs.uniform(0.92, 1.08))
         nz = np.random.default_rng([seed, 2, t]).integers(-noise, noise + 1, size=(h, w, 3), dtype=np.int8)
         out[t - t0] = np.clip(bases[s] + nz, 0, 255).astype(np.uint8)
     return out

@@ -281,3 +281,28 @@ def test_emu_pipe_host_path(emu):
     assert np.array_equal(r0, fh) and np.array_equal(r1, fh)
     assert emu.stb_pipe_wait(p, 7) != 0
     emu.stb_pipe_destroy(p)
+
+
+@pytest.mark.parametrize('h,w', [(60, 100), (97, 164), (46, 80)])
+def test_emu_border_tiles_ragged_sizes_and_fused_histogram(emu, h, w):
+    """Sizes where every tile of the TMA iteration kernels touches the image border and the right / bottom
+    tiles are ragged; the fused histogram must equal FlowHistogram of the flow the same call returns,
+    with and without materialising the flow; the two-launch pyramid is off (w % 32 != 0) or on."""
+    clip = synth.textured_clip(14, 3, h, w)
+    hd = C.c_void_p()
+    assert emu.stb_farneback_create(w, h, 2, None, C.byref(hd)) == 0
+    flows = [np.zeros((h, w, 2), np.float32) for _ in range(2)]
+    fh = np.zeros((2, 128), np.int32)
+    ft = _lib.ptr_table([f.ctypes.data for f in clip])
+    assert emu.stb_farneback_run_hist(hd, ft, 2, _lib.ptr_table([f.ctypes.data for f in flows]), P(fh), None) == 0, emu.stb_last_error()
+    fh_only = np.zeros((2, 128), np.int32)
+    assert emu.stb_farneback_run_hist(hd, ft, 2, None, P(fh_only), None) == 0
+    plain = [np.zeros((h, w, 2), np.float32) for _ in range(2)]
+    assert emu.stb_farneback_run(hd, ft, 2, _lib.ptr_table([f.ctypes.data for f in plain]), None) == 0
+    emu.stb_farneback_destroy(hd)
+    for i in range(2):
+        e = epe(flows[i], restate.optical_flow(clip[i], clip[i + 1]))
+        assert e.max() < 1e-4, (i, e.max())
+        assert np.array_equal(fh[i].reshape(2, 64), restate.flow_histogram(flows[i])), i
+        assert np.array_equal(plain[i], flows[i])
+    assert np.array_equal(fh_only, fh)
