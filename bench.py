@@ -677,7 +677,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--pairs', type=int, default=64, help='frame pairs per step and GPU')
-    ap.add_argument('--batch', type=int, default=16, help='pairs per C-ABI batch call')
+    ap.add_argument('--batch', type=int, default=32, help='pairs per C-ABI batch call')
     ap.add_argument('--no-extra', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-flow-frames', action='store_true', help='skip the e2e_flow_frames figure (2 GB of pinned memory)')

@@ -793,6 +793,49 @@ __device__ __forceinline__ void update_matrices_vpair(const float* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Block order of the kernels that read R (updmat_init_kernel and the iteration kernels): a 1-D grid
+// walked PAIR-FASTEST.  The polynomial expansion R of frame f+1 is read twice per level and pass:
+// displaced, as R1 of pair f, and in place, as R0 of pair f+1.  With the pair index as the slowest
+// grid dimension (round 1) those two reads were a whole pair (2.3 resident waves, ~200 MB of
+// traffic) apart and both came from HBM; with the pairs of one tile adjacent in the grid they run
+// at the same time on neighbouring SMs and the second read is an L2 hit: a quarter of the
+// iteration's 80 B/px never reaches HBM.  Order: pair, then `band` tile rows, then tile column,
+// then band, so a tile's vertical neighbours (whose M halos it shares) are co-resident too.
+// ---------------------------------------------------------------------------------------------
+struct TileOrder {
+  int tiles_x, tiles_y, np, band;     // band = tile rows walked before the column advances; 0 = round-1 order (x, y, pair);
+                                      // < 0 = 3-D grid (pair, tile x, tile y)
+};
+
+__device__ __forceinline__ void tile_decode(const TileOrder& o, int id, int& tx, int& ty, int& pz) {
+  if (o.band < 0) {   // experiment: 3-D grid (pair, tile x, tile y) in the hardware's own rasterisation order
+    const int per = o.np * o.tiles_x;
+    ty = id / per;
+    const int r = id - ty * per;
+    tx = r / o.np;
+    pz = r - tx * o.np;
+    return;
+  }
+  if (o.band <= 0) {
+    const int per = o.tiles_x * o.tiles_y;
+    pz = id / per;
+    const int r = id - pz * per;
+    ty = r / o.tiles_x;
+    tx = r - ty * o.tiles_x;
+    return;
+  }
+  const int per_band = o.tiles_x * o.band * o.np;
+  const int b = id / per_band, r = id - b * per_band;
+  const int bh = min(o.band, o.tiles_y - b * o.band);      // the last band may be shorter
+  const int col = bh * o.np;
+  tx = r / col;
+  const int r2 = r - tx * col;
+  const int tyb = r2 / o.np;
+  ty = b * o.band + tyb;
+  pz = r2 - tyb * o.np;
+}
+
 // initial M of a level from the up-sampled coarser flow (Appendix A.4-5).
 __device__ __forceinline__ void upsample_axis(int d, double scale, int n_src, int& s, float& f) {
   if (scale == 0.5) {   // exact halving: (d + 0.5) * 0.5 - 0.5 is exact in float, skip the double path
@@ -827,19 +870,27 @@ __device__ __forceinline__ float2 upsample_flow(const float2* __restrict__ fc, i
 __global__ void __launch_bounds__(256, 5)
 updmat_init_kernel(const float* __restrict__ R, const float* __restrict__ flow_coarse, float* __restrict__ M,
                    int w, int h, int wc, int hc, double scale_x, double scale_y, float flow_mul, int pair0,
-                   const STB_GRID_CONSTANT TmaMap3D map_R, int prefetch_rows) {
-  const int pair = pair0 + blockIdx.z;
-  if (prefetch_rows > 0 && threadIdx.x < 10) {
-    // Blocks are issued x-fastest, then y: the tile `prefetch_rows` block-rows further down is
-    // picked up about two resident waves from now.  Pull its R0 / R1 planes towards L2 so that
-    // block's loads hit L2 instead of waiting on DRAM (every line is prefetched by exactly one block).
-    int brow = (int)blockIdx.y + prefetch_rows, pz = pair;
-    if (brow >= (int)gridDim.y) { brow -= (int)gridDim.y; ++pz; }   // wraps into the next pair of this launch
-    if (brow < (int)gridDim.y && pz < pair0 + (int)gridDim.z)
-      tma_prefetch_l2(&map_R, (int)blockIdx.x * 64, brow * 8, pz * 5 + (int)threadIdx.x);
+                   const STB_GRID_CONSTANT TmaMap3D map_R, int prefetch_blocks, TileOrder ord) {
+  int btx, bty, bpz;
+  const int bid = (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+  tile_decode(ord, bid, btx, bty, bpz);
+  const int pair = pair0 + bpz;
+  if (prefetch_blocks > 0 && threadIdx.x < 10) {
+    // The block `prefetch_blocks` further on in the grid is picked up about two resident waves from
+    // now.  Pull its R planes towards L2 so its loads hit L2 instead of waiting on DRAM.  Every plane
+    // of every frame tile is prefetched by exactly one block: a block prefetches R0 (the planes of its
+    // own frame, lanes 0-4); the block of the launch's last pair also prefetches R1 (lanes 5-9) -- for
+    // the other pairs that frame is the R0 of the pair next to them.
+    const int ahead = bid + prefetch_blocks;
+    if (ahead < (int)(gridDim.x * gridDim.y * gridDim.z)) {
+      int atx, aty, apz;
+      tile_decode(ord, ahead, atx, aty, apz);
+      if ((int)threadIdx.x < 5 || ord.band <= 0 || apz == ord.np - 1)
+        tma_prefetch_l2(&map_R, atx * 64, aty * 8, (pair0 + apz) * 5 + (int)threadIdx.x);
+    }
   }
-  const int x = (blockIdx.x * 32 + (threadIdx.x & 31)) * 2;
-  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int x = (btx * 32 + (threadIdx.x & 31)) * 2;
+  const int y = bty * 8 + (threadIdx.x >> 5);
   if (x >= w || y >= h) return;
   const int n = w * h;
   const bool two = x + 1 < w;
@@ -1064,7 +1115,7 @@ constexpr int kFiFlStride = kFiTW + 1;        // float2 row stride of the staged
 template <bool UPDATE, bool HIST>
 __device__ __forceinline__ void iter15_global_phase(const float2* fl, unsigned* fh, float* __restrict__ Mout,
                                                     const float* __restrict__ R, const PtrBatch<float>& flow_out,
-                                                    int32_t* __restrict__ flow_hist, int w, int h, int pair, int ox0, int oy0) {
+                                                    int32_t* __restrict__ flow_hist, int w, int h, int pair, int pz, int ox0, int oy0) {
   const int tid = threadIdx.x, warp = tid >> 5;
   const size_t n = (size_t)w * h;
   const int ni = (int)n;
@@ -1105,8 +1156,8 @@ __device__ __forceinline__ void iter15_global_phase(const float2* fl, unsigned* 
     const float2 fb = fl[ty * kFiFlStride + tx + 1];
     const bool two = (x + 1 < w);
     const int o = y * w + x;
-    if (flow_out.p[blockIdx.z] != nullptr) {
-      float2* fo = reinterpret_cast<float2*>(flow_out.p[blockIdx.z]) + o;
+    if (flow_out.p[pz] != nullptr) {
+      float2* fo = reinterpret_cast<float2*>(flow_out.p[pz]) + o;
       if (two && pair_ok && ((reinterpret_cast<uintptr_t>(fo) & 15u) == 0)) {
         *reinterpret_cast<float4*>(fo) = make_float4(fa.x, fa.y, fb.x, fb.y);
       } else {
@@ -1164,7 +1215,7 @@ __device__ __forceinline__ float2 solve_flow15(float g11, float g12, float g22, 
 template <bool UPDATE, bool HIST>
 __global__ void __launch_bounds__(kFiThreads, 4)
 iter15_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const float* __restrict__ R,
-              PtrBatch<float> flow_out, int32_t* __restrict__ flow_hist, int w, int h, int pair0) {
+              PtrBatch<float> flow_out, int32_t* __restrict__ flow_hist, int w, int h, int pair0, TileOrder ord) {
   __shared__ float Vt[2][kFiVtWords];
   __shared__ float2 fl[kFiTH * kFiFlStride];
   __shared__ unsigned fh[HIST ? (kFiThreads / 32) * STB_FLOWHIST_INTS : 1];   // warp-private 128-bin tables
@@ -1173,10 +1224,13 @@ iter15_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const flo
   }
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int pair = pair0 + blockIdx.z;
+  int btx, bty, bpz;
+  const int bid = (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+  tile_decode(ord, bid, btx, bty, bpz);
+  const int pair = pair0 + bpz;
   const size_t n = (size_t)w * h;
   const float* Mp = Min + (size_t)pair * 5 * n;
-  const int ox0 = blockIdx.x * kFiTW, oy0 = blockIdx.y * kFiTH;
+  const int ox0 = btx * kFiTW, oy0 = bty * kFiTH;
 
   // vertical item of this thread
   // 64 thread slots per row group (62 active): a warp never straddles two groups, which would
@@ -1231,7 +1285,7 @@ iter15_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const flo
     fl[lane * kFiFlStride + warp * kFiGC + i] = solve_flow15(sums[0][i], sums[1][i], sums[2][i], sums[3][i], sums[4][i]);
   __syncthreads();
 
-  iter15_global_phase<UPDATE, HIST>(fl, fh, Mout, R, flow_out, flow_hist, w, h, pair, ox0, oy0);
+  iter15_global_phase<UPDATE, HIST>(fl, fh, Mout, R, flow_out, flow_hist, w, h, pair, bpz, ox0, oy0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1300,7 +1354,7 @@ template <bool UPDATE, bool HIST>
 __global__ void __launch_bounds__(kFiThreads, 4)
 iter15_tma_kernel(const STB_GRID_CONSTANT TmaMap3D map_in, float* __restrict__ Mout, const float* __restrict__ R,
                   PtrBatch<float> flow_out, int32_t* __restrict__ flow_hist, int w, int h, int pair0,
-                  const STB_GRID_CONSTANT TmaMap3D map_R, int prefetch_R) {
+                  const STB_GRID_CONSTANT TmaMap3D map_R, int prefetch_R, TileOrder ord) {
   __shared__ __align__(128) float raw[2][kTmStageFloats];     // also reused for the staged flow after the box phase
   __shared__ float Vt[2][kFiVtWords];
   __shared__ __align__(8) unsigned long long bars[2];
@@ -1310,8 +1364,11 @@ iter15_tma_kernel(const STB_GRID_CONSTANT TmaMap3D map_in, float* __restrict__ M
   static_assert(kFiRawW + 1 <= kTmRawW && (kFiTW % 4) == 0, "box covers the halo'd tile from an aligned origin");
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int pair = pair0 + blockIdx.z;
-  const int ox0 = blockIdx.x * kFiTW, oy0 = blockIdx.y * kFiTH;
+  int btx, bty, bpz;
+  const int bid = (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+  tile_decode(ord, bid, btx, bty, bpz);
+  const int pair = pair0 + bpz;
+  const int ox0 = btx * kFiTW, oy0 = bty * kFiTH;
   // box origin (may be negative).  The innermost TMA coordinate must be 16-byte aligned (measured:
   // an unaligned x traps), so the box starts one column early: raw column cx lives at box column cx+1.
   const int bx0 = ox0 - kFiM - 1, by0 = oy0 - kFiM;
@@ -1331,7 +1388,9 @@ iter15_tma_kernel(const STB_GRID_CONSTANT TmaMap3D map_in, float* __restrict__ M
     tma_load_tile(raw[0], &map_in, bx0, by0, pair * 5 + 0, &bars[0]);
     tma_load_tile(raw[1], &map_in, bx0, by0, pair * 5 + 1, &bars[1]);
   }
-  if (UPDATE && prefetch_R && tid >= 32 && tid < 42) {
+  // (pair-fastest order: R1 of this pair is the R0 of the pair next to it, whose block runs at the same time and
+  // prefetches it; only the launch's last pair has to pull its own R1)
+  if (UPDATE && prefetch_R && tid >= 32 && tid < ((ord.band <= 0 || bpz == ord.np - 1) ? 42 : 37)) {
     // the update phase at the end of this block reads this tile of R0 (frame `pair`) and, displaced
     // by the flow, of R1 (frame pair + 1): pull both towards L2 while the box phase runs, so those
     // loads find L2 hits instead of paying DRAM latency on the critical path (543 -> 522 us per
@@ -1393,7 +1452,7 @@ iter15_tma_kernel(const STB_GRID_CONSTANT TmaMap3D map_in, float* __restrict__ M
     fl[lane * kFiFlStride + warp * kFiGC + i] = solve_flow15(sums[0][i], sums[1][i], sums[2][i], sums[3][i], sums[4][i]);
   __syncthreads();
 
-  iter15_global_phase<UPDATE, HIST>(fl, fh, Mout, R, flow_out, flow_hist, w, h, pair, ox0, oy0);
+  iter15_global_phase<UPDATE, HIST>(fl, fh, Mout, R, flow_out, flow_hist, w, h, pair, bpz, ox0, oy0);
 }
 
 }  // namespace stb
@@ -1417,6 +1476,7 @@ struct stb_farneback {
   int fast_pyr;          // levels 1.. from one horizontal + one vertical launch (pyr_h_kernel / pyr_v_kernel)
   PyrTaps3 taps3;
   int init_prefetch_waves;   // updmat_init_kernel's prefetch distance in resident waves
+  int band_iter, band_init;  // TileOrder.band of the iteration kernels (tile rows of 32 px) / updmat_init_kernel (rows of 8 px); 0 = round-1 order
   // device workspace
   uint8_t* gray;    // [F][H*W]
   float* I;         // [F][N_k]      (N_0 sized)
@@ -1692,6 +1752,14 @@ int stb_farneback_create(int width, int height, int max_pairs, const stb_farneba
     for (int t = 0; t < 10; ++t) h->taps3.c2[t] = h->nscales > 2 ? h->merged[2].c[t] : 0.f;
     for (int t = 0; t < 20; ++t) h->taps3.c3[t] = h->nscales > 3 ? h->merged[3].c[t] : 0.f;
     h->init_prefetch_waves = 2;
+    // measured on B200 (1080p, 16-pair batches, one box, back to back): round-1 order through a 1-D grid 5117 fps;
+    // iteration kernels band 2 / 4 / 8 / all rows: 5284 / 5308 / 5317 / 5001; updmat_init_kernel band 8 / 16 / 32 /
+    // all rows: 5309 / 5308 / 5314 / 5193 and, as a 3-D grid (pair, tile x, tile y) in the hardware's own
+    // rasterisation order: +1.5 % on top (5466 vs 5383) -- the iteration kernels lose 0.4 % that way.
+    h->band_iter = 4;
+    h->band_init = -1;
+    if (const char* env = getenv("STB_BAND_ITER")) h->band_iter = atoi(env);
+    if (const char* env = getenv("STB_BAND_INIT")) h->band_init = atoi(env);
     if (const char* env = getenv("STB_INIT_PREFETCH_WAVES")) h->init_prefetch_waves = atoi(env);
   }
   if (const char* env = getenv("STB_CHUNKS")) {   // experiment knob: "c0,c1,c2,c3" pairs per launch per level
@@ -1904,10 +1972,12 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
       (void)F;
       {
         // prefetch distance: about two resident waves expressed in block rows
-        const int bx = ceil_div(w, 64);
-        const int ahead = h->prefetch_Ri[k] ? ceil_div(h->init_prefetch_waves * 4 * num_sms(), bx) : 0;
-        stb_launch(updmat_init_kernel, dim3(bx, ceil_div(hh, 8), np), dim3(256), 0, s, (const float*)h->R,
-                   coarse, h->M[0], w, hh, wc, hc, up_sx, up_sy, (float)(1. / h->prm.pyr_scale), p0, h->tmapRi[k], ahead);
+        const int bx = ceil_div(w, 64), by = ceil_div(hh, 8);
+        // prefetch distance: about `init_prefetch_waves` resident waves (5 blocks per SM) in blocks of the 1-D grid
+        const int ahead = h->prefetch_Ri[k] ? h->init_prefetch_waves * 4 * num_sms() : 0;
+        const TileOrder oi = {bx, by, np, h->band_init};
+        stb_launch(updmat_init_kernel, oi.band < 0 ? dim3(np, bx, by) : dim3((unsigned)(bx * by * np)), dim3(256), 0, s, (const float*)h->R,
+                   coarse, h->M[0], w, hh, wc, hc, up_sx, up_sy, (float)(1. / h->prm.pyr_scale), p0, h->tmapRi[k], ahead, oi);
       }
       STB_CHECK_LAUNCH("updmat_init_kernel");
       if (dbg && h->dbg_pair >= p0 && h->dbg_pair < p1) {
@@ -1925,7 +1995,8 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
       int mc = 0;
       const bool gauss = (h->prm.flags & kFlagGaussian) != 0;
       const bool fast15 = (m == kFiM) && !gauss;   // the winSize-15 kernels are box-window only
-      const dim3 grid = fast15 ? dim3(ceil_div(w, kFiTW), ceil_div(hh, kFiTH), np)
+      const TileOrder ot = {ceil_div(w, kFiTW), ceil_div(hh, kFiTH), np, h->band_iter};
+      const dim3 grid = fast15 ? (ot.band < 0 ? dim3(np, ot.tiles_x, ot.tiles_y) : dim3((unsigned)(ot.tiles_x * ot.tiles_y * np)))
                                : dim3(ceil_div(w, kItTW), ceil_div(hh, kItTH), np);
       const bool prof = h->profile && k == 0 && h->prm.num_iters > 1;
       for (int it = 0; it < h->prm.num_iters; ++it) {
@@ -1933,10 +2004,10 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
           if (prof && it == 0) { int prc = prof_mark(h, s); if (prc) return prc; }
           if (fast15 && h->use_tma[k])
             stb_launch(iter15_tma_kernel<true, false>, grid, dim3(kFiThreads), 0, s, h->tmap[mc][k], h->M[mc ^ 1],
-                       (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0, h->tmapR[k], h->prefetch_R[k]);
+                       (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0, h->tmapR[k], h->prefetch_R[k], ot);
           else if (fast15)
             stb_launch(iter15_kernel<true, false>, grid, dim3(kFiThreads), 0, s, (const float*)h->M[mc], h->M[mc ^ 1],
-                       (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0);
+                       (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0, ot);
           else if (gauss)
             stb_launch(iter_kernel<true, true>, grid, dim3(kItThreads), it_smem, s, (const float*)h->M[mc], h->M[mc ^ 1],
                        (const float*)h->R, fo, w, hh, m, p0, h->taps);
@@ -1953,16 +2024,16 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
         } else {
           if (fast15 && h->use_tma[k] && k == 0 && d_hist != nullptr)
             stb_launch(iter15_tma_kernel<false, true>, grid, dim3(kFiThreads), 0, s, h->tmap[mc][k], (float*)nullptr,
-                       (const float*)h->R, fo, d_hist, w, hh, p0, h->tmapR[k], 0);
+                       (const float*)h->R, fo, d_hist, w, hh, p0, h->tmapR[k], 0, ot);
           else if (fast15 && h->use_tma[k])
             stb_launch(iter15_tma_kernel<false, false>, grid, dim3(kFiThreads), 0, s, h->tmap[mc][k], (float*)nullptr,
-                       (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0, h->tmapR[k], 0);
+                       (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0, h->tmapR[k], 0, ot);
           else if (fast15 && k == 0 && d_hist != nullptr)
             stb_launch(iter15_kernel<false, true>, grid, dim3(kFiThreads), 0, s, (const float*)h->M[mc], (float*)nullptr,
-                       (const float*)h->R, fo, d_hist, w, hh, p0);
+                       (const float*)h->R, fo, d_hist, w, hh, p0, ot);
           else if (fast15)
             stb_launch(iter15_kernel<false, false>, grid, dim3(kFiThreads), 0, s, (const float*)h->M[mc], (float*)nullptr,
-                       (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0);
+                       (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0, ot);
           else if (gauss)
             stb_launch(iter_kernel<false, true>, grid, dim3(kItThreads), it_smem, s, (const float*)h->M[mc], (float*)nullptr,
                        (const float*)h->R, fo, w, hh, m, p0, h->taps);
