@@ -809,7 +809,15 @@ struct TileOrder {
 };
 
 __device__ __forceinline__ void tile_decode(const TileOrder& o, int id, int& tx, int& ty, int& pz) {
-  if (o.band < 0) {   // experiment: 3-D grid (pair, tile x, tile y) in the hardware's own rasterisation order
+  if (o.band == -2) {  // round-1 launch shape: 3-D grid (tile x, tile y, pair)
+    const int per = o.tiles_x * o.tiles_y;
+    pz = id / per;
+    const int r = id - pz * per;
+    ty = r / o.tiles_x;
+    tx = r - ty * o.tiles_x;
+    return;
+  }
+  if (o.band < 0) {   // 3-D grid (pair, tile x, tile y) in the hardware's own rasterisation order
     const int per = o.np * o.tiles_x;
     ty = id / per;
     const int r = id - ty * per;
@@ -885,7 +893,7 @@ updmat_init_kernel(const float* __restrict__ R, const float* __restrict__ flow_c
     if (ahead < (int)(gridDim.x * gridDim.y * gridDim.z)) {
       int atx, aty, apz;
       tile_decode(ord, ahead, atx, aty, apz);
-      if ((int)threadIdx.x < 5 || ord.band <= 0 || apz == ord.np - 1)
+      if ((int)threadIdx.x < 5 || ord.band == 0 || ord.band == -2 || apz == ord.np - 1)
         tma_prefetch_l2(&map_R, atx * 64, aty * 8, (pair0 + apz) * 5 + (int)threadIdx.x);
     }
   }
@@ -1390,7 +1398,7 @@ iter15_tma_kernel(const STB_GRID_CONSTANT TmaMap3D map_in, float* __restrict__ M
   }
   // (pair-fastest order: R1 of this pair is the R0 of the pair next to it, whose block runs at the same time and
   // prefetches it; only the launch's last pair has to pull its own R1)
-  if (UPDATE && prefetch_R && tid >= 32 && tid < ((ord.band <= 0 || bpz == ord.np - 1) ? 42 : 37)) {
+  if (UPDATE && prefetch_R && tid >= 32 && tid < ((ord.band == 0 || ord.band == -2 || bpz == ord.np - 1) ? 42 : 37)) {
     // the update phase at the end of this block reads this tile of R0 (frame `pair`) and, displaced
     // by the flow, of R1 (frame pair + 1): pull both towards L2 while the box phase runs, so those
     // loads find L2 hits instead of paying DRAM latency on the critical path (543 -> 522 us per
@@ -1480,7 +1488,12 @@ struct stb_farneback {
   // device workspace
   uint8_t* gray;    // [F][H*W]
   float* I;         // [F][N_k]      (N_0 sized)
-  float* R;         // [F][5][N_k]   (N_0 sized)
+  float* R;         // [F][5][N_0]   level 0 (and, before its expansion is written, the pyramid's intermediate)
+  float* Rk[kMaxScales];   // [F][5][N_k] per level: Rk[0] = R; separate buffers so that the expansions of all levels can be
+                           // produced ahead of (and concurrently with) the displacement iterations of the coarser levels
+  cudaStream_t s_prep;     // second lane: gray -> pyramid -> polynomial expansions of every level (low priority)
+  cudaEvent_t ev_fork, ev_R[kMaxScales];
+  int two_lanes;
   float* M[2];      // [P][5][N_k]   (N_0 sized)
   float* flow[2];   // [P][N_k*2]    level >= 1 only (N_1 sized)
   float* flow0;     // [P][N_0*2]    lazily allocated: level-0 flow when the caller wants only histograms
@@ -1645,7 +1658,7 @@ static bool make_tmap(TmaMap3D* m, float* base, int w, int h, int planes, int bo
 }
 #endif
 
-struct WsLayout { size_t gray, I, R, M, flow, total; };
+struct WsLayout { size_t gray, I, R, Rc, M, flow, total; };
 
 static WsLayout ws_layout(int W, int H, int P, int nscales, const int* ws, const int* hs) {
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
@@ -1655,9 +1668,11 @@ static WsLayout ws_layout(int W, int H, int P, int nscales, const int* ws, const
   l.gray = al(F * N0);
   l.I = al(F * N0 * sizeof(float));
   l.R = al(F * 5 * N0 * sizeof(float));
+  l.Rc = 0;                                        // R_1 .. R_3, each 256-byte aligned (8 / 16-byte vector accesses)
+  for (int k = 1; k < nscales; ++k) l.Rc += al(F * 5 * (size_t)ws[k] * hs[k] * sizeof(float));
   l.M = al((size_t)P * 5 * N0 * sizeof(float));
   l.flow = al((size_t)P * N1 * 2 * sizeof(float));
-  l.total = l.gray + l.I + l.R + 2 * l.M + 2 * l.flow;
+  l.total = l.gray + l.I + l.R + l.Rc + 2 * l.M + 2 * l.flow;
   return l;
 }
 
@@ -1785,6 +1800,15 @@ int stb_farneback_create(int width, int height, int max_pairs, const stb_farneba
   h->gray = base; off += l.gray;
   h->I = (float*)(base + off); off += l.I;
   h->R = (float*)(base + off); off += l.R;
+  h->Rk[0] = h->R;
+  {
+    size_t roff = off;
+    for (int k = 1; k < h->nscales; ++k) {
+      h->Rk[k] = (float*)(base + roff);
+      roff += ((size_t)(max_pairs + 1) * 5 * h->w[k] * h->h[k] * sizeof(float) + 255) & ~(size_t)255;
+    }
+    off += l.Rc;
+  }
   h->M[0] = (float*)(base + off); off += l.M;
   h->M[1] = (float*)(base + off); off += l.M;
   h->flow[0] = (float*)(base + off); off += l.flow;
@@ -1800,10 +1824,10 @@ int stb_farneback_create(int width, int height, int max_pairs, const stb_farneba
           make_tmap(&h->tmap[1][k], h->M[1], h->w[k], h->h[k], 5 * max_pairs))
         h->use_tma[k] = 1;
       if (h->use_tma[k] && !getenv("STB_NO_R_PREFETCH") && h->h[k] >= kPfBoxH &&
-          make_tmap(&h->tmapR[k], h->R, h->w[k], h->h[k], 5 * (max_pairs + 1), kPfBoxW, kPfBoxH))
+          make_tmap(&h->tmapR[k], h->Rk[k], h->w[k], h->h[k], 5 * (max_pairs + 1), kPfBoxW, kPfBoxH))
         h->prefetch_R[k] = 1;
       if (!(no_tma && no_tma[0] == '1') && !getenv("STB_NO_INIT_PREFETCH") &&
-          make_tmap(&h->tmapRi[k], h->R, h->w[k], h->h[k], 5 * (max_pairs + 1), 64, kPfInitBoxH))
+          make_tmap(&h->tmapRi[k], h->Rk[k], h->w[k], h->h[k], 5 * (max_pairs + 1), 64, kPfInitBoxH))
         h->prefetch_Ri[k] = 1;
     }
   }
@@ -1823,12 +1847,31 @@ int stb_farneback_create(int width, int height, int max_pairs, const stb_farneba
     return cuda_fail(e, "cudaFuncSetAttribute");
   }
 #endif
+  {
+    // second lane for the pyramid / polynomial-expansion chain (see run_levels); lowest priority, so the
+    // displacement-iteration chain is scheduled first whenever both have blocks ready
+    h->two_lanes = getenv("STB_ONE_LANE") ? 0 : 1;
+    int lo = 0, hi = 0;
+    cudaError_t e2 = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (e2 == cudaSuccess) e2 = cudaStreamCreateWithPriority(&h->s_prep, cudaStreamNonBlocking, lo);
+    if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    for (int k = 0; k < kMaxScales && e2 == cudaSuccess; ++k) e2 = cudaEventCreateWithFlags(&h->ev_R[k], cudaEventDisableTiming);
+    if (e2 != cudaSuccess) {
+      int rc2 = cuda_fail(e2, "stb_farneback_create: second lane");
+      stb_farneback_destroy(h);
+      return rc2;
+    }
+  }
   *out = h;
   return STB_OK;
 }
 
 int stb_farneback_destroy(stb_farneback* h) {
   if (!h) return STB_OK;
+  if (h->s_prep) { cudaStreamSynchronize(h->s_prep); cudaStreamDestroy(h->s_prep); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (int k = 0; k < kMaxScales; ++k)
+    if (h->ev_R[k]) cudaEventDestroy(h->ev_R[k]);
   if (h->gray) cudaFree(h->gray);
   if (h->flow0) cudaFree(h->flow0);
   for (cudaEvent_t e : h->ev_free) cudaEventDestroy(e);
@@ -1898,6 +1941,57 @@ static inline bool fused_hist_available(const stb_farneback* h) {
 
 // d_hist != NULL: fused FlowHistogram (n*128 int32, pre-zeroed) when the winSize-15 kernel runs;
 // returns through *hist_fused whether it did.  d_flow entries may be NULL only in that case.
+// I_k and R_k of frames [fa, fb) at level k on stream `sp` (the "prep" work of a level)
+static int prep_level(stb_farneback* h, int k, int fa, int fb, bool fastpyr, cudaStream_t sp) {
+  const int w = h->w[k], hh = h->h[k];
+  const size_t nk = (size_t)w * hh;
+  const size_t N0 = (size_t)h->W * h->H;
+  const PyrParams& pp = h->pyr[k];
+  size_t i_off = 0;
+  if (fastpyr) for (int j = 1; j < k; ++j) i_off += (size_t)h->w[j] * h->h[j];
+  const float* Ik = h->I + i_off;
+  const size_t i_stride = (fastpyr && k >= 1) ? N0 : nk;
+  if (fastpyr && k >= 1) {
+    // I_k already produced by pyr_h_kernel / pyr_v_kernel
+  } else if (k == 0) {
+    // rows of the gray plane and of I are 4/16-byte aligned iff W % 4 == 0 (bases are 256-byte aligned)
+    stb_launch(pyr0_kernel, dim3(ceil_div(w, 128), ceil_div(hh, 32), fb - fa), dim3(256), 0, sp,
+               (const uint8_t*)h->gray, h->I, w, hh, pp.taps[0], pp.taps[1], pp.taps[2], fa, (w % 4 == 0) ? 1 : 0);
+    STB_CHECK_LAUNCH("pyr0_kernel");
+  } else if (h->pow2[k]) {
+    const dim3 g(ceil_div(w, 32), ceil_div(hh, k == 3 ? 8 : 16), fb - fa);
+    if (k == 1) stb_launch(pyr_pow2_kernel<1>, g, dim3(256), 0, sp, (const uint8_t*)h->gray, h->I, h->W, h->H, h->merged[k], fa);
+    else if (k == 2) stb_launch(pyr_pow2_kernel<2>, g, dim3(256), 0, sp, (const uint8_t*)h->gray, h->I, h->W, h->H, h->merged[k], fa);
+    else stb_launch(pyr_pow2_kernel<3>, g, dim3(256), 0, sp, (const uint8_t*)h->gray, h->I, h->W, h->H, h->merged[k], fa);
+    STB_CHECK_LAUNCH("pyr_pow2_kernel");
+  } else {
+    const size_t pyr_smem = (size_t)pp.max_rows * kPyrTW * sizeof(float);
+    stb_launch(pyr_kernel, dim3(ceil_div(w, kPyrTW), ceil_div(hh, kPyrTH), fb - fa), dim3(kPyrThreads), pyr_smem, sp,
+               (const uint8_t*)h->gray, h->I, pp, fa);
+    STB_CHECK_LAUNCH("pyr_kernel");
+  }
+  if (h->prm.poly_n == kPolyN)
+    stb_launch(polyexp_kernel, dim3(ceil_div(w, kPeTW), ceil_div(hh, kPeTH), fb - fa), dim3(kPeThreads), 0, sp,
+               Ik, i_stride, h->Rk[k], w, hh, h->pc, fa);
+  else
+    stb_launch(polyexp_generic_kernel, dim3(ceil_div(w, 32), ceil_div(hh, 8), fb - fa), dim3(256), 0, sp,
+               Ik, i_stride, h->Rk[k], w, hh, h->pc, h->prm.poly_n, fa);
+  STB_CHECK_LAUNCH("polyexp_kernel");
+  return STB_OK;
+}
+
+// d_hist != NULL: fused FlowHistogram (n*128 int32, pre-zeroed) when the winSize-15 kernel runs;
+// returns through *hist_fused whether it did.  d_flow entries may be NULL only in that case.
+//
+// Schedule.  A level needs (a) I_k and the polynomial expansion R_k of every frame -- which depend on the
+// gray planes only -- and (b) the chain updmat_init -> iterations, which depends on R_k and on the coarser
+// level's flow.  When the whole batch fits one launch per level, (a) for ALL levels runs on the handle's own
+// low-priority stream (forked from the caller's stream after the gray conversion, every R_k in its own
+// buffer) while the caller's stream walks the chain (b) from the coarsest level, waiting per level on an
+// event: the small, latency-bound launches of the coarse levels (less than one resident wave at level 3)
+// share the GPU with the bandwidth-heavy expansion of the fine levels instead of running alone.  The lanes
+// join before the call returns control of the stream.  Batches that need several chunks per level (more
+// than 64 pairs per call) and the debug taps use the single-lane order.
 static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_t s, int32_t* d_hist = nullptr,
                       bool* hist_fused = nullptr) {
   if (hist_fused) *hist_fused = (d_hist != nullptr) && fused_hist_available(h);
@@ -1905,21 +1999,36 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
   const int m = h->prm.win_size / 2;
   const size_t it_smem = iter_smem_bytes(m);
   int fl_cur = 0;  // h->flow[fl_cur] receives this level's flow (levels >= 1)
-  // Levels >= 1 of all n + 1 frames from two launches (the intermediate lives in the R buffer, which is
-  // not written before the first polynomial expansion; I_1.. are packed into the I buffer, which level 0
+  // Levels >= 1 of all n + 1 frames from two launches (the intermediate lives in the level-0 R buffer, which is
+  // not written before the level-0 polynomial expansion; I_1.. are packed into the I buffer, which level 0
   // only overwrites after they have been consumed).  Needs the batch in one chunk at every level.
-  bool fastpyr = h->fast_pyr != 0;
-  for (int k = 0; k < h->nscales; ++k) fastpyr = fastpyr && n <= h->chunk[k];
+  bool one_chunk = true;
+  for (int k = 0; k < h->nscales; ++k) one_chunk = one_chunk && n <= h->chunk[k];
+  const bool fastpyr = h->fast_pyr != 0 && one_chunk;
+  const bool lanes = h->two_lanes != 0 && one_chunk && h->dbg_level < 0;
   const size_t N0 = (size_t)h->W * h->H;
+  cudaStream_t sp = s;
+  if (lanes) {
+    sp = h->s_prep;
+    STB_CUDA(cudaEventRecord(h->ev_fork, s));            // gray planes ready; the previous call on `s` is done with R / I
+    STB_CUDA(cudaStreamWaitEvent(sp, h->ev_fork, 0));
+  }
   if (fastpyr) {
     const int nlev = h->nscales - 1;
     const int items = (h->W >> 5) * h->H;
-    stb_launch(pyr_h_kernel, dim3(ceil_div(items, 128), F), dim3(128), 0, s, (const uint8_t*)h->gray, h->R, h->W, h->H, h->taps3, nlev, 0);
+    stb_launch(pyr_h_kernel, dim3(ceil_div(items, 128), F), dim3(128), 0, sp, (const uint8_t*)h->gray, h->R, h->W, h->H, h->taps3, nlev, 0);
     STB_CHECK_LAUNCH("pyr_h_kernel");
     int quads = 0;
     for (int k = 1; k <= nlev; ++k) quads += (h->w[k] >> 2) * h->h[k];
-    stb_launch(pyr_v_kernel, dim3(ceil_div(quads, 128), F), dim3(128), 0, s, (const float*)h->R, h->I, h->W, h->H, h->taps3, nlev, N0, 0);
+    stb_launch(pyr_v_kernel, dim3(ceil_div(quads, 128), F), dim3(128), 0, sp, (const float*)h->R, h->I, h->W, h->H, h->taps3, nlev, N0, 0);
     STB_CHECK_LAUNCH("pyr_v_kernel");
+  }
+  if (lanes) {
+    for (int k = h->nscales - 1; k >= 0; --k) {
+      int prc = prep_level(h, k, 0, F, fastpyr, sp);
+      if (prc) return prc;
+      STB_CUDA(cudaEventRecord(h->ev_R[k], sp));
+    }
   }
   for (int k = h->nscales - 1; k >= 0; --k) {
     const int w = h->w[k], hh = h->h[k];
@@ -1929,44 +2038,21 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
     if (fastpyr) for (int j = 1; j < k; ++j) i_off += (size_t)h->w[j] * h->h[j];
     const float* Ik = h->I + i_off;
     const size_t i_stride = (fastpyr && k >= 1) ? N0 : nk;
-    const PyrParams& pp = h->pyr[k];
+    const float* Rk = h->Rk[k];
     const float* coarse = (k == h->nscales - 1) ? nullptr : h->flow[fl_cur ^ 1];
     const int wc = coarse ? h->w[k + 1] : 0, hc = coarse ? h->h[k + 1] : 0;
     const double up_sx = coarse ? 1. / ((double)w / wc) : 0, up_sy = coarse ? 1. / ((double)hh / hc) : 0;
     int frames_done = 0;
     const bool dbg = (h->dbg_level == k);
+    if (lanes) STB_CUDA(cudaStreamWaitEvent(s, h->ev_R[k], 0));
     for (int p0 = 0; p0 < n; p0 += h->chunk[k]) {
       const int p1 = (p0 + h->chunk[k] < n) ? p0 + h->chunk[k] : n;
       const int np = p1 - p0;
       // frames [fa, fb) still need I_k and R_k
       const int fa = frames_done, fb = p1 + 1;
-      if (fb > fa) {
-        if (fastpyr && k >= 1) {
-          // already there
-        } else if (k == 0) {
-          // rows of the gray plane and of I are 4/16-byte aligned iff W % 4 == 0 (bases are 256-byte aligned)
-          stb_launch(pyr0_kernel, dim3(ceil_div(w, 128), ceil_div(hh, 32), fb - fa), dim3(256), 0, s,
-                     (const uint8_t*)h->gray, h->I, w, hh, pp.taps[0], pp.taps[1], pp.taps[2], fa, (w % 4 == 0) ? 1 : 0);
-          STB_CHECK_LAUNCH("pyr0_kernel");
-        } else if (h->pow2[k]) {
-          const dim3 g(ceil_div(w, 32), ceil_div(hh, k == 3 ? 8 : 16), fb - fa);
-          if (k == 1) stb_launch(pyr_pow2_kernel<1>, g, dim3(256), 0, s, (const uint8_t*)h->gray, h->I, h->W, h->H, h->merged[k], fa);
-          else if (k == 2) stb_launch(pyr_pow2_kernel<2>, g, dim3(256), 0, s, (const uint8_t*)h->gray, h->I, h->W, h->H, h->merged[k], fa);
-          else stb_launch(pyr_pow2_kernel<3>, g, dim3(256), 0, s, (const uint8_t*)h->gray, h->I, h->W, h->H, h->merged[k], fa);
-          STB_CHECK_LAUNCH("pyr_pow2_kernel");
-        } else {
-          const size_t pyr_smem = (size_t)pp.max_rows * kPyrTW * sizeof(float);
-          stb_launch(pyr_kernel, dim3(ceil_div(w, kPyrTW), ceil_div(hh, kPyrTH), fb - fa), dim3(kPyrThreads), pyr_smem, s,
-                     (const uint8_t*)h->gray, h->I, pp, fa);
-          STB_CHECK_LAUNCH("pyr_kernel");
-        }
-        if (h->prm.poly_n == kPolyN)
-          stb_launch(polyexp_kernel, dim3(ceil_div(w, kPeTW), ceil_div(hh, kPeTH), fb - fa), dim3(kPeThreads), 0, s,
-                     Ik, i_stride, h->R, w, hh, h->pc, fa);
-        else
-          stb_launch(polyexp_generic_kernel, dim3(ceil_div(w, 32), ceil_div(hh, 8), fb - fa), dim3(256), 0, s,
-                     Ik, i_stride, h->R, w, hh, h->pc, h->prm.poly_n, fa);
-        STB_CHECK_LAUNCH("polyexp_kernel");
+      if (fb > fa && !lanes) {
+        int prc = prep_level(h, k, fa, fb, fastpyr, s);
+        if (prc) return prc;
         frames_done = fb;
       }
       (void)F;
@@ -1976,7 +2062,7 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
         // prefetch distance: about `init_prefetch_waves` resident waves (5 blocks per SM) in blocks of the 1-D grid
         const int ahead = h->prefetch_Ri[k] ? h->init_prefetch_waves * 4 * num_sms() : 0;
         const TileOrder oi = {bx, by, np, h->band_init};
-        stb_launch(updmat_init_kernel, oi.band < 0 ? dim3(np, bx, by) : dim3((unsigned)(bx * by * np)), dim3(256), 0, s, (const float*)h->R,
+        stb_launch(updmat_init_kernel, oi.band == -2 ? dim3(bx, by, np) : oi.band < 0 ? dim3(np, bx, by) : dim3((unsigned)(bx * by * np)), dim3(256), 0, s, Rk,
                    coarse, h->M[0], w, hh, wc, hc, up_sx, up_sy, (float)(1. / h->prm.pyr_scale), p0, h->tmapRi[k], ahead, oi);
       }
       STB_CHECK_LAUNCH("updmat_init_kernel");
@@ -1984,8 +2070,8 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
         const int dp = h->dbg_pair;
         if (h->dbg_I0) STB_CUDA(cudaMemcpyAsync(h->dbg_I0, Ik + (size_t)dp * i_stride, nk * 4, cudaMemcpyDeviceToDevice, s));
         if (h->dbg_I1) STB_CUDA(cudaMemcpyAsync(h->dbg_I1, Ik + (size_t)(dp + 1) * i_stride, nk * 4, cudaMemcpyDeviceToDevice, s));
-        if (h->dbg_R0) STB_CUDA(cudaMemcpyAsync(h->dbg_R0, h->R + (size_t)dp * 5 * nk, nk * 20, cudaMemcpyDeviceToDevice, s));
-        if (h->dbg_R1) STB_CUDA(cudaMemcpyAsync(h->dbg_R1, h->R + (size_t)(dp + 1) * 5 * nk, nk * 20, cudaMemcpyDeviceToDevice, s));
+        if (h->dbg_R0) STB_CUDA(cudaMemcpyAsync(h->dbg_R0, Rk + (size_t)dp * 5 * nk, nk * 20, cudaMemcpyDeviceToDevice, s));
+        if (h->dbg_R1) STB_CUDA(cudaMemcpyAsync(h->dbg_R1, Rk + (size_t)(dp + 1) * 5 * nk, nk * 20, cudaMemcpyDeviceToDevice, s));
         if (h->dbg_M0) STB_CUDA(cudaMemcpyAsync(h->dbg_M0, h->M[0] + (size_t)dp * 5 * nk, nk * 20, cudaMemcpyDeviceToDevice, s));
       }
       PtrBatch<float> fo;
@@ -1996,7 +2082,8 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
       const bool gauss = (h->prm.flags & kFlagGaussian) != 0;
       const bool fast15 = (m == kFiM) && !gauss;   // the winSize-15 kernels are box-window only
       const TileOrder ot = {ceil_div(w, kFiTW), ceil_div(hh, kFiTH), np, h->band_iter};
-      const dim3 grid = fast15 ? (ot.band < 0 ? dim3(np, ot.tiles_x, ot.tiles_y) : dim3((unsigned)(ot.tiles_x * ot.tiles_y * np)))
+      const dim3 grid = fast15 ? (ot.band == -2 ? dim3(ot.tiles_x, ot.tiles_y, np)
+                                                : ot.band < 0 ? dim3(np, ot.tiles_x, ot.tiles_y) : dim3((unsigned)(ot.tiles_x * ot.tiles_y * np)))
                                : dim3(ceil_div(w, kItTW), ceil_div(hh, kItTH), np);
       const bool prof = h->profile && k == 0 && h->prm.num_iters > 1;
       for (int it = 0; it < h->prm.num_iters; ++it) {
@@ -2004,16 +2091,16 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
           if (prof && it == 0) { int prc = prof_mark(h, s); if (prc) return prc; }
           if (fast15 && h->use_tma[k])
             stb_launch(iter15_tma_kernel<true, false>, grid, dim3(kFiThreads), 0, s, h->tmap[mc][k], h->M[mc ^ 1],
-                       (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0, h->tmapR[k], h->prefetch_R[k], ot);
+                       Rk, fo, (int32_t*)nullptr, w, hh, p0, h->tmapR[k], h->prefetch_R[k], ot);
           else if (fast15)
             stb_launch(iter15_kernel<true, false>, grid, dim3(kFiThreads), 0, s, (const float*)h->M[mc], h->M[mc ^ 1],
-                       (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0, ot);
+                       Rk, fo, (int32_t*)nullptr, w, hh, p0, ot);
           else if (gauss)
             stb_launch(iter_kernel<true, true>, grid, dim3(kItThreads), it_smem, s, (const float*)h->M[mc], h->M[mc ^ 1],
-                       (const float*)h->R, fo, w, hh, m, p0, h->taps);
+                       Rk, fo, w, hh, m, p0, h->taps);
           else
             stb_launch(iter_kernel<true, false>, grid, dim3(kItThreads), it_smem, s, (const float*)h->M[mc], h->M[mc ^ 1],
-                       (const float*)h->R, fo, w, hh, m, p0, h->taps);
+                       Rk, fo, w, hh, m, p0, h->taps);
           mc ^= 1;
           if (prof && it == h->prm.num_iters - 2) {
             int prc = prof_mark(h, s);
@@ -2024,22 +2111,22 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
         } else {
           if (fast15 && h->use_tma[k] && k == 0 && d_hist != nullptr)
             stb_launch(iter15_tma_kernel<false, true>, grid, dim3(kFiThreads), 0, s, h->tmap[mc][k], (float*)nullptr,
-                       (const float*)h->R, fo, d_hist, w, hh, p0, h->tmapR[k], 0, ot);
+                       Rk, fo, d_hist, w, hh, p0, h->tmapR[k], 0, ot);
           else if (fast15 && h->use_tma[k])
             stb_launch(iter15_tma_kernel<false, false>, grid, dim3(kFiThreads), 0, s, h->tmap[mc][k], (float*)nullptr,
-                       (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0, h->tmapR[k], 0, ot);
+                       Rk, fo, (int32_t*)nullptr, w, hh, p0, h->tmapR[k], 0, ot);
           else if (fast15 && k == 0 && d_hist != nullptr)
             stb_launch(iter15_kernel<false, true>, grid, dim3(kFiThreads), 0, s, (const float*)h->M[mc], (float*)nullptr,
-                       (const float*)h->R, fo, d_hist, w, hh, p0, ot);
+                       Rk, fo, d_hist, w, hh, p0, ot);
           else if (fast15)
             stb_launch(iter15_kernel<false, false>, grid, dim3(kFiThreads), 0, s, (const float*)h->M[mc], (float*)nullptr,
-                       (const float*)h->R, fo, (int32_t*)nullptr, w, hh, p0, ot);
+                       Rk, fo, (int32_t*)nullptr, w, hh, p0, ot);
           else if (gauss)
             stb_launch(iter_kernel<false, true>, grid, dim3(kItThreads), it_smem, s, (const float*)h->M[mc], (float*)nullptr,
-                       (const float*)h->R, fo, w, hh, m, p0, h->taps);
+                       Rk, fo, w, hh, m, p0, h->taps);
           else
             stb_launch(iter_kernel<false, false>, grid, dim3(kItThreads), it_smem, s, (const float*)h->M[mc], (float*)nullptr,
-                       (const float*)h->R, fo, w, hh, m, p0, h->taps);
+                       Rk, fo, w, hh, m, p0, h->taps);
         }
         STB_CHECK_LAUNCH("iter_kernel");
       }

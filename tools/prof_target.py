@@ -14,10 +14,11 @@ from scannertools_b200 import ops, synth  # noqa: E402
 def main():
     what = sys.argv[1:] or ['flow', 'hist', 'flowhist']
     npairs = int(os.environ.get('PROF_PAIRS', '2'))
-    base = synth.textured_clip(1, 5, 1080, 1920)
+    W, H = int(os.environ.get('PROF_W', '1920')), int(os.environ.get('PROF_H', '1080'))
+    base = synth.textured_clip(1, 5, H, W)
     clip = np.concatenate([base] * ((npairs + 5) // 5 + 1))[:npairs + 1]
     fr = torch.from_numpy(clip).cuda()
-    of = ops.OpticalFlow(1920, 1080, max_batch=npairs)
+    of = ops.OpticalFlow(W, H, max_batch=npairs)
     f4k = torch.randint(0, 256, (8, 2160, 3840, 3), dtype=torch.uint8, device='cuda')
     flow = torch.randn((4, 1080, 1920, 2), device='cuda') * 5
 
