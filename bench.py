@@ -556,9 +556,10 @@ def extra_workloads(torch, dist, ops, lib, args, rank, world, barrier, reduce_ma
     state = {}
 
     def c4_step():
-        prev = ops.histogram(halo)[0] if halo is not None else None
-        state['h'] = ops.histogram(fr)
-        state['S'] = ops.shot_scores(state['h'], prev_hist=prev)
+        # one launch over this rank's frames and, for shards that do not start the clip, the halo frame in front of them
+        hall = ops.histogram(fr_all)
+        state['h'] = hall[f0 - a0:]
+        state['S'] = ops.shot_scores(state['h'], prev_hist=hall[0] if halo is not None else None)
     t = time_dev(c4_step, 10)
     S_local = state['S'].cpu().numpy()
     pipe = ops.Pipe(3840, 2160, max_batch=7)

@@ -216,6 +216,11 @@ STB_API int stb_pipe_flow(stb_pipe* p, const uint8_t* h_frames, int n, float* h_
 STB_API int stb_pipe_flow_async(stb_pipe* p, const uint8_t* h_frames, int n, float* h_flow, int32_t* h_flow_hist,
                                 int* ticket);
 STB_API int stb_pipe_wait(stb_pipe* p, int ticket);
+/* Page-locked host staging memory for the calls above (they are only asynchronous on pinned buffers).
+ * write_combined != 0 allocates write-combined memory (cudaHostAllocWriteCombined): fast for the device
+ * to read over PCIe, slow for the host to read back -- for upload-only frame buffers. */
+STB_API int stb_host_alloc(size_t bytes, int write_combined, void** out);
+STB_API int stb_host_free(void* p);
 
 #ifdef __cplusplus
 }

@@ -60,6 +60,8 @@ SIGNATURES = {
     'stb_pipe_flow': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     'stb_pipe_flow_async': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.POINTER(C.c_int)]),
     'stb_pipe_wait': (C.c_int, [_vp, C.c_int]),
+    'stb_host_alloc': (C.c_int, [C.c_size_t, C.c_int, C.POINTER(_vp)]),
+    'stb_host_free': (C.c_int, [_vp]),
 }
 
 

@@ -844,6 +844,14 @@ __device__ __forceinline__ void tile_decode(const TileOrder& o, int id, int& tx,
   pz = r2 - tyb * o.np;
 }
 
+// this block's tile: 3-D grids map blockIdx directly (no integer division)
+__device__ __forceinline__ void tile_of_block(const TileOrder& o, int& tx, int& ty, int& pz, int& bid) {
+  bid = (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+  if (o.band == -1) { pz = (int)blockIdx.x; tx = (int)blockIdx.y; ty = (int)blockIdx.z; }
+  else if (o.band == -2) { tx = (int)blockIdx.x; ty = (int)blockIdx.y; pz = (int)blockIdx.z; }
+  else tile_decode(o, bid, tx, ty, pz);
+}
+
 // initial M of a level from the up-sampled coarser flow (Appendix A.4-5).
 __device__ __forceinline__ void upsample_axis(int d, double scale, int n_src, int& s, float& f) {
   if (scale == 0.5) {   // exact halving: (d + 0.5) * 0.5 - 0.5 is exact in float, skip the double path
@@ -880,8 +888,8 @@ updmat_init_kernel(const float* __restrict__ R, const float* __restrict__ flow_c
                    int w, int h, int wc, int hc, double scale_x, double scale_y, float flow_mul, int pair0,
                    const STB_GRID_CONSTANT TmaMap3D map_R, int prefetch_blocks, TileOrder ord) {
   int btx, bty, bpz;
-  const int bid = (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
-  tile_decode(ord, bid, btx, bty, bpz);
+  int bid;
+  tile_of_block(ord, btx, bty, bpz, bid);
   const int pair = pair0 + bpz;
   if (prefetch_blocks > 0 && threadIdx.x < 10) {
     // The block `prefetch_blocks` further on in the grid is picked up about two resident waves from
@@ -907,8 +915,33 @@ updmat_init_kernel(const float* __restrict__ R, const float* __restrict__ flow_c
     const float2* fc = reinterpret_cast<const float2*>(flow_coarse) + (size_t)pair * wc * hc;
     int sy; float fy;
     upsample_axis(y, scale_y, hc, sy, fy);
-    da = upsample_flow(fc, wc, hc, sy, fy, x, scale_x, flow_mul);
-    if (two) db = upsample_flow(fc, wc, hc, sy, fy, x + 1, scale_x, flow_mul);
+    const int cx = x >> 1;
+    if (scale_x == 0.5 && two && cx >= 1 && cx + 1 < wc) {
+      // Exact halving, interior: pixel x = 2 cx reads coarse columns (cx - 1, cx) with weights (0.25, 0.75) and
+      // pixel x + 1 columns (cx, cx + 1) with (0.75, 0.25) -- upsample_axis's results -- so the pair shares the
+      // middle column: 6 loads instead of 8, same arithmetic per pixel as upsample_flow.
+      const int sy1 = min(sy + 1, hc - 1);
+      const float2* r0 = fc + (sy * wc + cx - 1);
+      const float2* r1 = fc + (sy1 * wc + cx - 1);
+      const float2 t0 = __ldg(r0), t1 = __ldg(r0 + 1), t2 = __ldg(r0 + 2);
+      const float2 u0 = __ldg(r1), u1 = __ldg(r1 + 1), u2 = __ldg(r1 + 2);
+      const float ay0 = 1.f - fy;
+      {
+        const float fx = 0.75f, ax0 = 0.25f;
+        const float h0x = t0.x * ax0 + t1.x * fx, h1x = u0.x * ax0 + u1.x * fx;
+        const float h0y = t0.y * ax0 + t1.y * fx, h1y = u0.y * ax0 + u1.y * fx;
+        da = make_float2((h0x * ay0 + h1x * fy) * flow_mul, (h0y * ay0 + h1y * fy) * flow_mul);
+      }
+      {
+        const float fx = 0.25f, ax0 = 0.75f;
+        const float h0x = t1.x * ax0 + t2.x * fx, h1x = u1.x * ax0 + u2.x * fx;
+        const float h0y = t1.y * ax0 + t2.y * fx, h1y = u1.y * ax0 + u2.y * fx;
+        db = make_float2((h0x * ay0 + h1x * fy) * flow_mul, (h0y * ay0 + h1y * fy) * flow_mul);
+      }
+    } else {
+      da = upsample_flow(fc, wc, hc, sy, fy, x, scale_x, flow_mul);
+      if (two) db = upsample_flow(fc, wc, hc, sy, fy, x + 1, scale_x, flow_mul);
+    }
   }
   const float* R0 = R + (size_t)pair * 5 * n;
   const float* R1 = R0 + (size_t)5 * n;
@@ -1233,8 +1266,8 @@ iter15_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const flo
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int btx, bty, bpz;
-  const int bid = (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
-  tile_decode(ord, bid, btx, bty, bpz);
+  int bid;
+  tile_of_block(ord, btx, bty, bpz, bid);
   const int pair = pair0 + bpz;
   const size_t n = (size_t)w * h;
   const float* Mp = Min + (size_t)pair * 5 * n;
@@ -1373,8 +1406,8 @@ iter15_tma_kernel(const STB_GRID_CONSTANT TmaMap3D map_in, float* __restrict__ M
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int btx, bty, bpz;
-  const int bid = (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
-  tile_decode(ord, bid, btx, bty, bpz);
+  int bid;
+  tile_of_block(ord, btx, bty, bpz, bid);
   const int pair = pair0 + bpz;
   const int ox0 = btx * kFiTW, oy0 = bty * kFiTH;
   // box origin (may be negative).  The innermost TMA coordinate must be 16-byte aligned (measured:

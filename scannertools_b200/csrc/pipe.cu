@@ -6,6 +6,7 @@
 // Pass page-locked host memory for the copies to be truly asynchronous.
 #include "stb_rt.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -246,6 +247,35 @@ int stb_pipe_flow(stb_pipe* p, const uint8_t* h_frames, int n, float* h_flow, in
   int rc = stb_pipe_flow_async(p, h_frames, n, h_flow, h_flow_hist, &ticket);
   if (rc || ticket < 0) return rc;
   return stb_pipe_wait(p, ticket);
+}
+
+int stb_host_alloc(size_t bytes, int write_combined, void** out) {
+  if (!out || bytes == 0) { set_error("stb_host_alloc: invalid argument"); return STB_ERR_INVALID; }
+  *out = nullptr;
+#ifdef STB_CPU_EMU
+  *out = std::calloc(1, bytes);
+  return *out ? STB_OK : STB_ERR_ALLOC;
+#else
+  cudaError_t e = cudaHostAlloc(out, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    *out = nullptr;
+    set_error("stb_host_alloc: cudaHostAlloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    return ((int)e == 100 || (int)e == 35) ? STB_ERR_NO_DEVICE : STB_ERR_ALLOC;
+  }
+  return STB_OK;
+#endif
+}
+
+int stb_host_free(void* p) {
+  if (!p) return STB_OK;
+#ifdef STB_CPU_EMU
+  std::free(p);
+  return STB_OK;
+#else
+  STB_CUDA(cudaFreeHost(p));
+  return STB_OK;
+#endif
 }
 
 }  // extern "C"

@@ -27,7 +27,8 @@ def main():
             continue
         if r and r[0] == 'Line No':
             hdr = r
-            i_inst, i_smp, i_wf = hdr.index('Instructions Executed'), hdr.index('# Samples'), hdr.index('L1 Wavefronts Shared')
+            i_inst, i_smp = hdr.index('Instructions Executed'), hdr.index('# Samples')
+            i_wf = hdr.index('L1 Wavefronts Shared') if 'L1 Wavefronts Shared' in hdr else None
             continue
         if hdr is None or len(r) < 10:
             continue
@@ -41,7 +42,7 @@ def main():
         n = num(r[i_inst])
         agg[cur_line] += n
         samp[cur_line] += num(r[i_smp])
-        shw[cur_line] += num(r[i_wf])
+        shw[cur_line] += num(r[i_wf]) if i_wf is not None else 0
         tot += n
     print('total warp instructions', tot, ' stall samples', sum(samp.values()), ' shared wavefronts', sum(shw.values()))
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:top]:
