@@ -624,17 +624,33 @@ def extra_workloads(torch, dist, ops, lib, args, rank, world, barrier, reduce_ma
     clips = [torch.from_numpy(synth.textured_clip(300 + sid, fps_batch + 1, 720, 1280)).cuda() for sid in mine]
     handles = [ops.OpticalFlow(1280, 720, max_batch=fps_batch) for _ in mine]
 
+    # every video stream runs on its own CUDA stream (a 64-stream deployment has one evaluator per stream): the
+    # coarse, latency-bound pyramid levels of one stream overlap the fine levels of another
+    cstreams = [torch.cuda.Stream() for _ in mine]
+
     def c5_step():
+        cur = torch.cuda.current_stream()
+        for k in range(len(mine)):
+            cstreams[k].wait_stream(cur)
+            with torch.cuda.stream(cstreams[k]):
+                handles[k].execute_with_histogram(clips[k], want_flow=False, stream=cstreams[k])
+                ops.histogram(clips[k][:fps_batch], stream=cstreams[k])
+        for k in range(len(mine)):
+            cur.wait_stream(cstreams[k])
+    t = time_dev(c5_step, 5, warm=2)
+
+    def c5_step_serial():
         for k in range(len(mine)):
             handles[k].execute_with_histogram(clips[k], want_flow=False)
             ops.histogram(clips[k][:fps_batch])
-    t = time_dev(c5_step, 5, warm=2)
+    t_serial = time_dev(c5_step_serial, 5, warm=1)
     for hnd in handles:
         hnd.close()
     frames = world * n_streams * fps_batch
     out['c5_mixed_720p'] = {'workload': 'C5: %d concurrent 1280x720 streams (%d per GPU, whole streams pinned to GPUs), OpticalFlow+FlowHistogram '
                                         'and RGB Histogram, %d frames per stream per step' % (n_streams * world, n_streams, fps_batch),
-                            'value': frames / t, 'unit': 'frames/s', 'ms_per_step': t * 1e3, 'roofline': roof(frames, C5_BYTES, t)}
+                            'value': frames / t, 'unit': 'frames/s', 'ms_per_step': t * 1e3, 'roofline': roof(frames, C5_BYTES, t),
+                            'one_cuda_stream_for_all_frames_per_s': frames / t_serial}
     return out if rank == 0 else {}
 
 

@@ -1503,6 +1503,7 @@ iter15_tma_kernel(const STB_GRID_CONSTANT TmaMap3D map_in, float* __restrict__ M
 // =============================================================================================
 using namespace stb;
 
+namespace stb { struct FbGraph; static void graph_free(FbGraph* g); }
 struct stb_farneback {
   int W, H, max_pairs, device;
   stb_farneback_params prm;
@@ -1527,6 +1528,10 @@ struct stb_farneback {
   cudaStream_t s_prep;     // second lane: gray -> pyramid -> polynomial expansions of every level (low priority)
   cudaEvent_t ev_fork, ev_R[kMaxScales];
   int two_lanes;
+  // CUDA-graph replay of a whole batch (see graph_run): one instantiated graph per (pairs, outputs) shape
+  int use_graph;
+  cudaStream_t s_cap;
+  std::vector<stb::FbGraph*> graphs;
   float* M[2];      // [P][5][N_k]   (N_0 sized)
   float* flow[2];   // [P][N_k*2]    level >= 1 only (N_1 sized)
   float* flow0;     // [P][N_0*2]    lazily allocated: level-0 flow when the caller wants only histograms
@@ -1884,9 +1889,11 @@ int stb_farneback_create(int width, int height, int max_pairs, const stb_farneba
     // second lane for the pyramid / polynomial-expansion chain (see run_levels); lowest priority, so the
     // displacement-iteration chain is scheduled first whenever both have blocks ready
     h->two_lanes = getenv("STB_ONE_LANE") ? 0 : 1;
+    h->use_graph = getenv("STB_NO_GRAPH") ? 0 : 1;
     int lo = 0, hi = 0;
     cudaError_t e2 = cudaDeviceGetStreamPriorityRange(&lo, &hi);
     if (e2 == cudaSuccess) e2 = cudaStreamCreateWithPriority(&h->s_prep, cudaStreamNonBlocking, lo);
+    if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&h->s_cap, cudaStreamNonBlocking);
     if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     for (int k = 0; k < kMaxScales && e2 == cudaSuccess; ++k) e2 = cudaEventCreateWithFlags(&h->ev_R[k], cudaEventDisableTiming);
     if (e2 != cudaSuccess) {
@@ -1902,6 +1909,9 @@ int stb_farneback_create(int width, int height, int max_pairs, const stb_farneba
 int stb_farneback_destroy(stb_farneback* h) {
   if (!h) return STB_OK;
   if (h->s_prep) { cudaStreamSynchronize(h->s_prep); cudaStreamDestroy(h->s_prep); }
+  if (h->s_cap) cudaStreamDestroy(h->s_cap);
+  for (FbGraph* g : h->graphs) graph_free(g);
+  h->graphs.clear();
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (int k = 0; k < kMaxScales; ++k)
     if (h->ev_R[k]) cudaEventDestroy(h->ev_R[k]);
@@ -2208,6 +2218,191 @@ static int to_gray(stb_farneback* h, const uint8_t* const* d_rgb, int F, cudaStr
   return STB_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// CUDA-graph replay.  A batch is ~25 launches on two lanes; at small resolutions (640x480, 720p
+// streams) the launches are a few microseconds each and the per-launch CPU + front-end cost shows.
+// The first call of a given shape (number of pairs, which outputs) is stream-captured -- the very
+// same enqueue code, fork / join of the second lane included -- and instantiated; later calls of
+// that shape patch the kernel nodes that carry caller pointers (gray_kernel: the frame table; the
+// level-0 last-iteration kernel: the flow table and the histogram pointer; the histogram memset)
+// and replay the graph with one cudaGraphLaunch.  Everything else in the graph only touches
+// handle-owned workspace.  Not used with the debug taps, the event profiler, chunked batches
+// (> 64 pairs) or parameter sets that need the unfused histogram kernel.
+// ---------------------------------------------------------------------------------------------
+#ifndef STB_CPU_EMU
+struct GrayArgs { PtrBatch<const uint8_t> frames; uint8_t* gray; unsigned long long npx; };
+struct LastArgs {
+  TmaMap3D map_in; float* Mout; const float* R; PtrBatch<float> flow_out; int32_t* flow_hist;
+  int w, h, pair0; TmaMap3D map_R; int prefetch_R; TileOrder ord;
+};
+struct FbGraph {
+  int n, kind;                       // kind: 0 = flow frames, 1 = flow frames + histogram, 2 = histogram only
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  std::vector<cudaGraphNode_t> gray_nodes;
+  std::vector<cudaKernelNodeParams> gray_np;
+  std::vector<GrayArgs> gray_args;
+  cudaGraphNode_t last_node = nullptr;
+  cudaKernelNodeParams last_np;
+  LastArgs last_args;
+  cudaGraphNode_t memset_node = nullptr;
+  cudaMemsetParams memset_p;
+  long long kernel_nodes = 0;
+};
+
+static void graph_free(FbGraph* g) {
+  if (!g) return;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  delete g;
+}
+
+static bool graph_eligible(const stb_farneback* h, int n) {
+  if (!h->use_graph || h->profile || h->dbg_level >= 0 || !h->s_cap) return false;
+  if (!fused_hist_available(h) || !h->use_tma[0]) return false;
+  for (int k = 0; k < h->nscales; ++k)
+    if (n > h->chunk[k]) return false;
+  return n + 1 <= kMaxPtrBatch;      // one gray launch
+}
+
+// enqueue of one batch on `s` (shared by the direct path and the capture)
+static int enqueue_batch(stb_farneback* h, const uint8_t* const* d_rgb, int n, float* const* fl, int32_t* d_hist, cudaStream_t s) {
+  int rc = to_gray(h, d_rgb, n + 1, s);
+  if (rc) return rc;
+  if (d_hist) {
+    cudaError_t e = cudaMemsetAsync(d_hist, 0, (size_t)n * STB_FLOWHIST_INTS * sizeof(int32_t), s);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(flow_hist)");
+  }
+  return run_levels(h, n, fl, s, d_hist, nullptr);
+}
+
+static int graph_build(stb_farneback* h, const uint8_t* const* d_rgb, int n, float* const* fl, int32_t* d_hist, int kind, FbGraph** out) {
+  *out = nullptr;
+  FbGraph* g = new (std::nothrow) FbGraph();
+  if (!g) { set_error("out of host memory"); return STB_ERR_ALLOC; }
+  g->n = n; g->kind = kind;
+  const long long l0 = g_launches.load(std::memory_order_relaxed);
+  cudaError_t e = cudaStreamBeginCapture(h->s_cap, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) { graph_free(g); return cuda_fail(e, "cudaStreamBeginCapture"); }
+  int rc = enqueue_batch(h, d_rgb, n, fl, d_hist, h->s_cap);
+  e = cudaStreamEndCapture(h->s_cap, &g->graph);
+  g_launches.store(l0, std::memory_order_relaxed);           // nothing ran: the capture only recorded
+  if (rc || e != cudaSuccess || !g->graph) {
+    graph_free(g);
+    (void)cudaGetLastError();
+    return rc ? rc : cuda_fail(e, "cudaStreamEndCapture");
+  }
+  size_t nn = 0;
+  e = cudaGraphGetNodes(g->graph, nullptr, &nn);
+  std::vector<cudaGraphNode_t> nodes(nn);
+  if (e == cudaSuccess && nn) e = cudaGraphGetNodes(g->graph, nodes.data(), &nn);
+  const void* f_last = kind == 0 ? (const void*)iter15_tma_kernel<false, false> : (const void*)iter15_tma_kernel<false, true>;
+  for (size_t i = 0; i < nn && e == cudaSuccess; ++i) {
+    cudaGraphNodeType ty;
+    e = cudaGraphNodeGetType(nodes[i], &ty);
+    if (e != cudaSuccess) break;
+    if (ty == cudaGraphNodeTypeKernel) {
+      ++g->kernel_nodes;
+      cudaKernelNodeParams kp;
+      e = cudaGraphKernelNodeGetParams(nodes[i], &kp);
+      if (e != cudaSuccess) break;
+      if (kp.func == (void*)gray_kernel) {
+        // (the graph's parameter copies carry no alignment guarantee: memcpy, never a typed load)
+        GrayArgs a;
+        std::memcpy(&a.frames, kp.kernelParams[0], sizeof(a.frames));
+        std::memcpy(&a.gray, kp.kernelParams[1], sizeof(a.gray));
+        std::memcpy(&a.npx, kp.kernelParams[2], sizeof(a.npx));
+        g->gray_nodes.push_back(nodes[i]); g->gray_np.push_back(kp); g->gray_args.push_back(a);
+      } else if (kp.func == f_last) {
+        int pw = 0, ph = 0;
+        std::memcpy(&pw, kp.kernelParams[5], sizeof(int));
+        std::memcpy(&ph, kp.kernelParams[6], sizeof(int));
+        if (pw != h->w[0] || ph != h->h[0]) continue;            // the last iteration of a coarser level
+        LastArgs& a = g->last_args;
+        std::memcpy(&a.map_in, kp.kernelParams[0], sizeof(a.map_in));
+        std::memcpy(&a.Mout, kp.kernelParams[1], sizeof(a.Mout));
+        std::memcpy(&a.R, kp.kernelParams[2], sizeof(a.R));
+        std::memcpy(&a.flow_out, kp.kernelParams[3], sizeof(a.flow_out));
+        std::memcpy(&a.flow_hist, kp.kernelParams[4], sizeof(a.flow_hist));
+        a.w = pw; a.h = ph;
+        std::memcpy(&a.pair0, kp.kernelParams[7], sizeof(a.pair0));
+        std::memcpy(&a.map_R, kp.kernelParams[8], sizeof(a.map_R));
+        std::memcpy(&a.prefetch_R, kp.kernelParams[9], sizeof(a.prefetch_R));
+        std::memcpy(&a.ord, kp.kernelParams[10], sizeof(a.ord));
+        g->last_node = nodes[i]; g->last_np = kp;
+      }
+    } else if (ty == cudaGraphNodeTypeMemset) {
+      g->memset_node = nodes[i];
+      e = cudaGraphMemsetNodeGetParams(nodes[i], &g->memset_p);
+    }
+  }
+  // exactly the nodes we know how to re-point, or no graph at all
+  const bool ok = e == cudaSuccess && g->gray_nodes.size() == 1 && g->last_node && ((d_hist != nullptr) == (g->memset_node != nullptr));
+  if (ok) e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+  if (!ok || e != cudaSuccess) {
+    graph_free(g);
+    (void)cudaGetLastError();
+    return STB_OK;      // *out stays NULL: the caller falls back to direct launches
+  }
+  *out = g;
+  return STB_OK;
+}
+
+// returns STB_OK with *used = true when the batch was enqueued through a graph
+static int graph_run(stb_farneback* h, const uint8_t* const* d_rgb, int n, float* const* fl, int32_t* d_hist, int kind, cudaStream_t s,
+                     bool* used) {
+  *used = false;
+  if (!graph_eligible(h, n)) return STB_OK;
+  FbGraph* g = nullptr;
+  for (FbGraph* c : h->graphs)
+    if (c->n == n && c->kind == kind) { g = c; break; }
+  if (!g) {
+    for (int i = 0; i <= n; ++i)
+      if (!d_rgb[i]) { set_error("stb_farneback_run: frame %d is NULL", i); return STB_ERR_INVALID; }
+    int rc = graph_build(h, d_rgb, n, fl, d_hist, kind, &g);
+    if (rc) return rc;
+    if (!g) { h->use_graph = 0; return STB_OK; }       // capture not possible here: stay on direct launches
+    if (h->graphs.size() >= 16) { graph_free(h->graphs.front()); h->graphs.erase(h->graphs.begin()); }
+    h->graphs.push_back(g);
+  }
+  {
+    GrayArgs& a = g->gray_args[0];
+    for (int i = 0; i < kMaxPtrBatch; ++i) a.frames.p[i] = nullptr;
+    for (int i = 0; i <= n; ++i) {
+      if (!d_rgb[i]) { set_error("stb_farneback_run: frame %d is NULL", i); return STB_ERR_INVALID; }
+      a.frames.p[i] = d_rgb[i];
+    }
+    void* args[3] = {&a.frames, &a.gray, &a.npx};
+    cudaKernelNodeParams kp = g->gray_np[0];
+    kp.kernelParams = args; kp.extra = nullptr;
+    STB_CUDA(cudaGraphExecKernelNodeSetParams(g->exec, g->gray_nodes[0], &kp));
+  }
+  {
+    LastArgs& a = g->last_args;
+    for (int i = 0; i < kMaxPtrBatch; ++i) a.flow_out.p[i] = i < n ? fl[i] : nullptr;
+    a.flow_hist = d_hist;
+    void* args[11] = {&a.map_in, &a.Mout, &a.R, &a.flow_out, &a.flow_hist, &a.w, &a.h, &a.pair0, &a.map_R, &a.prefetch_R, &a.ord};
+    cudaKernelNodeParams kp = g->last_np;
+    kp.kernelParams = args; kp.extra = nullptr;
+    STB_CUDA(cudaGraphExecKernelNodeSetParams(g->exec, g->last_node, &kp));
+  }
+  if (g->memset_node) {
+    cudaMemsetParams mp = g->memset_p;
+    mp.dst = d_hist;
+    STB_CUDA(cudaGraphExecMemsetNodeSetParams(g->exec, g->memset_node, &mp));
+  }
+  STB_CUDA(cudaGraphLaunch(g->exec, s));
+  g_launches.fetch_add(g->kernel_nodes, std::memory_order_relaxed);
+  *used = true;
+  return STB_OK;
+}
+#else
+struct FbGraph {};
+static void graph_free(FbGraph*) {}
+static int graph_run(stb_farneback*, const uint8_t* const*, int, float* const*, int32_t*, int, cudaStream_t, bool* used) { *used = false; return STB_OK; }
+#endif
+
 }  // namespace stb
 
 extern "C" {
@@ -2220,6 +2415,9 @@ int stb_farneback_run(stb_farneback* h, const uint8_t* const* d_rgb, int n, floa
   for (int i = 0; i < n; ++i)
     if (!d_flow[i]) { set_error("stb_farneback_run: d_flow[%d] is NULL", i); return STB_ERR_INVALID; }
   cudaStream_t s = (cudaStream_t)stream;
+  bool via_graph = false;
+  rc = graph_run(h, d_rgb, n, d_flow, nullptr, 0, s, &via_graph);
+  if (rc || via_graph) return rc;
   rc = to_gray(h, d_rgb, n + 1, s);
   if (rc) return rc;
   return run_levels(h, n, d_flow, s);
@@ -2262,6 +2460,11 @@ int stb_farneback_run_hist(stb_farneback* h, const uint8_t* const* d_rgb, int n,
     rc = ensure_flow0(h);
     if (rc) { delete[] heap; return rc; }
     for (int i = 0; i < n; ++i) fl[i] = h->flow0 + (size_t)i * h->W * h->H * 2;
+  }
+  if (fused) {
+    bool via_graph = false;
+    rc = graph_run(h, d_rgb, n, fl, d_flow_hist, d_flow ? 1 : 2, s, &via_graph);
+    if (rc || via_graph) { delete[] heap; return rc; }
   }
   rc = to_gray(h, d_rgb, n + 1, s);
   if (!rc && fused) {

@@ -188,7 +188,10 @@ shot_scores_kernel(const int32_t* __restrict__ hist, int n, const int32_t* __res
 // FlowHistogram: 64-bin magnitude [0,64) + 64-bin angle [0,360) of an HxWx2 f32 flow field.
 // Arithmetic reproduces OpenCV's cartToPolar (polynomial fastAtan, angleInDegrees) and
 // calcHist's double-precision bin index bit-for-bit.
-// Per-lane private 16-bit counters packed two per word: [warp][64 words][lane].
+// Per-lane private 16-bit counters packed two per word: [table][64 words][lane], one table per four warps
+// (bank == lane, so a warp's updates never conflict whatever the content; two warps only collide when they hit
+// the same (bin, lane) word in the same cycle).  Round 1 kept one table per warp (64 KB, 3 blocks per SM, 34 %
+// occupancy, 0.32-0.35 of HBM, latency-bound); 16 KB per block lets six blocks be resident.
 // -------------------------------------------------------------------------------------------
 struct PtrAddrF32 {
   PtrBatch<const float> t;
@@ -204,8 +207,11 @@ struct StrideAddrF32 {
 
 constexpr int kFlowHistThreads = 256;
 constexpr int kFlowHistWarps = kFlowHistThreads / 32;
-constexpr int kFlowHistSmemWords = kFlowHistWarps * 64 * 32;  // 64 KB
-constexpr unsigned kFlowHistMaxPxPerThread = 32768;           // 16-bit counters cannot overflow
+constexpr int kFlowHistWarpsPerTable = 4;
+constexpr int kFlowHistTables = kFlowHistWarps / kFlowHistWarpsPerTable;
+constexpr int kFlowHistSmemWords = kFlowHistTables * 64 * 32;  // 16 KB
+constexpr int kFlowHistBlocksPerSM = 6;
+constexpr unsigned kFlowHistMaxPxPerThread = 8192;            // x 4 warps per table: 16-bit counters cannot overflow
 
 __device__ __forceinline__ void flow_count(unsigned* my, float x, float y) {
   int bm, ba;
@@ -215,7 +221,7 @@ __device__ __forceinline__ void flow_count(unsigned* my, float x, float y) {
 }
 
 template <class Addr>
-__global__ void __launch_bounds__(kFlowHistThreads, 3)
+__global__ void __launch_bounds__(kFlowHistThreads, kFlowHistBlocksPerSM)
 flow_hist_kernel(Addr addr, unsigned long long npx, int32_t* __restrict__ out, unsigned base_blocks, unsigned rem) {
   // 1-D grid over (frame, part), as in hist_rgb16_kernel
   unsigned frame, part, nparts;
@@ -228,7 +234,7 @@ flow_hist_kernel(Addr addr, unsigned long long npx, int32_t* __restrict__ out, u
   }
   __syncthreads();
   const float* f = addr(frame);
-  unsigned* my = sh + warp * (64 * 32) + lane;
+  unsigned* my = sh + (warp / kFlowHistWarpsPerTable) * (64 * 32) + lane;
   const unsigned long long gt = (unsigned long long)part * kFlowHistThreads + tid;
   const unsigned long long T = (unsigned long long)nparts * kFlowHistThreads;
   if ((reinterpret_cast<uintptr_t>(f) & 15u) == 0) {
@@ -259,7 +265,7 @@ flow_hist_kernel(Addr addr, unsigned long long npx, int32_t* __restrict__ out, u
   const unsigned shift = (bin & 1u) * 16u;
   unsigned s = 0;
 #pragma unroll
-  for (int w = 0; w < kFlowHistWarps; ++w) {
+  for (int w = 0; w < kFlowHistTables; ++w) {
     const unsigned* row = sh + (w * 64 + word) * 32 + rpart * 16;
 #pragma unroll
     for (int l = 0; l < 16; l += 4) {
@@ -358,7 +364,7 @@ static int launch_flow_hist(Addr addr, int n, unsigned long long npx, int32_t* d
                                   (int)(kFlowHistSmemWords * sizeof(unsigned))));
     attr_done[dev] = true;
   }
-  const int wave = num_sms() * 3;
+  const int wave = num_sms() * kFlowHistBlocksPerSM;
   const long long max_useful = (long long)((npx / 2 + (unsigned long long)kFlowHistThreads * 2 - 1) / ((unsigned long long)kFlowHistThreads * 2));
   const long long min_needed = (long long)((npx + (unsigned long long)kFlowHistThreads * kFlowHistMaxPxPerThread - 1) /
                                            ((unsigned long long)kFlowHistThreads * kFlowHistMaxPxPerThread));
