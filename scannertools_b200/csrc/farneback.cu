@@ -38,7 +38,65 @@ constexpr int kMaxPolyN = 7;   // polyN = 5 (the reference) has the tiled kernel
 struct PolyConsts {
   float g[kMaxPolyN + 1], xg[kMaxPolyN + 1], xxg[kMaxPolyN + 1];
   float ig11, ig03, ig33, ig55;
+  // the taps duplicated into (t, t) pairs: 64-bit constant-bank operands of the packed f32x2 vertical pass
+  float2 g2[kMaxPolyN + 1], xg2[kMaxPolyN + 1], xxg2[kMaxPolyN + 1];
 };
+
+// packed f32x2 arithmetic (sm_100a FADD2 / FMUL2 / FFMA2): two independent IEEE single-precision operations per
+// instruction, same rounding as the scalar forms
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) {
+#ifdef STB_CPU_EMU
+  return make_float2(a.x + b.x, a.y + b.y);
+#else
+  unsigned long long ra, rb, rc;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rc));
+  return r;
+#endif
+}
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) {
+#ifdef STB_CPU_EMU
+  return make_float2(a.x - b.x, a.y - b.y);
+#else
+  unsigned long long ra, rb, rc;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rc));
+  return r;
+#endif
+}
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) {
+#ifdef STB_CPU_EMU
+  return make_float2(a.x * b.x, a.y * b.y);
+#else
+  unsigned long long ra, rb, rc;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rc));
+  return r;
+#endif
+}
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) {   // a * b + c
+#ifdef STB_CPU_EMU
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#else
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rd));
+  return r;
+#endif
+}
 
 struct PyrParams {
   int W, H;          // full resolution
@@ -497,6 +555,53 @@ polyexp_kernel(const float* __restrict__ I, size_t i_stride, float* __restrict__
   float* dst = R + (size_t)frame * 5 * n;
   const int ox0 = blockIdx.x * kPeTW, oy0 = blockIdx.y * kPeTH;
 
+  if ((w & 1) == 0) {
+    // Column PAIRS (x, x + 1), x even: one 8-byte load per row and packed f32x2 arithmetic -- half the instructions
+    // of the scalar pass below, the same operations per element.  38 pairs cover columns ox0 - 6 .. ox0 + 69 (the
+    // tile's 64 + 5 either side, plus one spare column each end that the horizontal pass never reads).
+    constexpr int kPairs = (kPeCols + 2) / 2;   // 38
+    for (int item = tid; item < kPairs * (kPeTH / 8); item += kPeThreads) {
+      const int g = item / kPairs, q = item - g * kPairs;
+      const int xa = ox0 + 2 * q - (kPolyN + 1);            // even
+      const int y_first = oy0 + g * 8 - kPolyN;
+      float2 v[kPeRows];
+      const bool rows_in = y_first >= 0 && y_first + kPeRows - 1 <= h - 1;
+      if (xa >= 0 && xa + 1 < w) {
+        if (rows_in) {
+          const float* p = src + y_first * w + xa;
+#pragma unroll
+          for (int j = 0; j < kPeRows; ++j) v[j] = __ldg(reinterpret_cast<const float2*>(p + j * w));
+        } else {
+#pragma unroll
+          for (int j = 0; j < kPeRows; ++j) v[j] = __ldg(reinterpret_cast<const float2*>(src + min(max(y_first + j, 0), h - 1) * w + xa));
+        }
+      } else {
+        const int x0c = min(max(xa, 0), w - 1), x1c = min(max(xa + 1, 0), w - 1);    // replicate columns
+#pragma unroll
+        for (int j = 0; j < kPeRows; ++j) {
+          const float* row = src + min(max(y_first + j, 0), h - 1) * w;
+          v[j] = make_float2(__ldg(row + x0c), __ldg(row + x1c));
+        }
+      }
+      const int col = 2 * q + 2;          // x = ox0 - 8 + col
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float2 r0 = f2mul(v[i + kPolyN], c.g2[0]);
+        float2 r1 = make_float2(0.f, 0.f), r2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 1; k <= kPolyN; ++k) {
+          const float2 a = v[i + kPolyN - k], b = v[i + kPolyN + k];
+          const float2 pp = f2add(a, b);
+          r0 = f2fma(c.g2[k], pp, r0);
+          r1 = f2fma(c.xg2[k], f2sub(b, a), r1);
+          r2 = f2fma(c.xxg2[k], pp, r2);
+        }
+        *reinterpret_cast<float2*>(&V[0][g * 8 + i][col]) = r0;
+        *reinterpret_cast<float2*>(&V[1][g * 8 + i][col]) = r1;
+        *reinterpret_cast<float2*>(&V[2][g * 8 + i][col]) = r2;
+      }
+    }
+  } else
   for (int item = tid; item < kPeCols * (kPeTH / 8); item += kPeThreads) {
     const int g = item / kPeCols, cx = item - g * kPeCols;
     const int x = min(max(ox0 + cx - kPolyN, 0), w - 1);
@@ -883,7 +988,8 @@ __device__ __forceinline__ float2 upsample_flow(const float2* __restrict__ fc, i
 // kernel measured 12 % slower here (495 vs 440 us per 16-pair level-0 launch).
 // 5 blocks/SM (48 registers, no spills): with the prefetch-ahead in place the extra resident warps are
 // worth +1 % of the step (before it, 5 blocks/SM measured slower: 500 vs 440 us in isolation).
-__global__ void __launch_bounds__(256, 5)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 updmat_init_kernel(const float* __restrict__ R, const float* __restrict__ flow_coarse, float* __restrict__ M,
                    int w, int h, int wc, int hc, double scale_x, double scale_y, float flow_mul, int pair0,
                    const STB_GRID_CONSTANT TmaMap3D map_R, int prefetch_blocks, TileOrder ord) {
@@ -1518,6 +1624,7 @@ struct stb_farneback {
   int fast_pyr;          // levels 1.. from one horizontal + one vertical launch (pyr_h_kernel / pyr_v_kernel)
   PyrTaps3 taps3;
   int init_prefetch_waves;   // updmat_init_kernel's prefetch distance in resident waves
+  int init_minb;             // experiment knob: updmat_init_kernel's minimum blocks per SM (register cap 48 / 64 / 80)
   int band_iter, band_init;  // TileOrder.band of the iteration kernels (tile rows of 32 px) / updmat_init_kernel (rows of 8 px); 0 = round-1 order
   // device workspace
   uint8_t* gray;    // [F][H*W]
@@ -1611,6 +1718,9 @@ static bool poly_consts(int n, double sigma, PolyConsts* pc) {
     pc->g[x] = gf[x + n];
     pc->xg[x] = (float)(x * gf[x + n]);
     pc->xxg[x] = (float)(x * x * gf[x + n]);
+    pc->g2[x] = make_float2(pc->g[x], pc->g[x]);
+    pc->xg2[x] = make_float2(pc->xg[x], pc->xg[x]);
+    pc->xxg2[x] = make_float2(pc->xxg[x], pc->xxg[x]);
   }
   double G[6][6] = {}, inv[6][6];
   for (int y = -n; y <= n; ++y)
@@ -1811,6 +1921,8 @@ int stb_farneback_create(int width, int height, int max_pairs, const stb_farneba
     // rasterisation order: +1.5 % on top (5466 vs 5383) -- the iteration kernels lose 0.4 % that way.
     h->band_iter = 4;
     h->band_init = -1;
+    h->init_minb = 5;
+    if (const char* env = getenv("STB_INIT_MINB")) h->init_minb = atoi(env);
     if (const char* env = getenv("STB_BAND_ITER")) h->band_iter = atoi(env);
     if (const char* env = getenv("STB_BAND_INIT")) h->band_init = atoi(env);
     if (const char* env = getenv("STB_INIT_PREFETCH_WAVES")) h->init_prefetch_waves = atoi(env);
@@ -2105,7 +2217,8 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
         // prefetch distance: about `init_prefetch_waves` resident waves (5 blocks per SM) in blocks of the 1-D grid
         const int ahead = h->prefetch_Ri[k] ? h->init_prefetch_waves * 4 * num_sms() : 0;
         const TileOrder oi = {bx, by, np, h->band_init};
-        stb_launch(updmat_init_kernel, oi.band == -2 ? dim3(bx, by, np) : oi.band < 0 ? dim3(np, bx, by) : dim3((unsigned)(bx * by * np)), dim3(256), 0, s, Rk,
+        auto* init_fn = h->init_minb == 4 ? updmat_init_kernel<4> : (h->init_minb == 3 ? updmat_init_kernel<3> : updmat_init_kernel<5>);
+        stb_launch(init_fn, oi.band == -2 ? dim3(bx, by, np) : oi.band < 0 ? dim3(np, bx, by) : dim3((unsigned)(bx * by * np)), dim3(256), 0, s, Rk,
                    coarse, h->M[0], w, hh, wc, hc, up_sx, up_sy, (float)(1. / h->prm.pyr_scale), p0, h->tmapRi[k], ahead, oi);
       }
       STB_CHECK_LAUNCH("updmat_init_kernel");
