@@ -502,6 +502,58 @@ pyr0_kernel(const uint8_t* __restrict__ gray, float* __restrict__ I, int W, int 
   }
 }
 
+// Level 0 again, for W % 8 == 0: a thread owns 8 pixels x 4 rows.  Six 8-byte row loads (the 4 rows + one above
+// and below, REFLECT_101), the two horizontal halo bytes of every row come from the neighbouring lanes by shuffle
+// (lanes 0 / 31 and the image edges load them), bytes are converted to float once, the separable 3x3 runs in
+// registers in the same fmaf order as pyr0_kernel (bit-identical), four rows of two 16-byte stores.  About a
+// third of pyr0_kernel's instructions per pixel (that kernel spends them on per-byte halo loads and per-row
+// border arithmetic for a 4 x 4 patch).
+__global__ void __launch_bounds__(256)
+pyr0x8_kernel(const uint8_t* __restrict__ gray, float* __restrict__ I, int W, int H, float t0, float t1, float t2, int frame0) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int frame = frame0 + blockIdx.z;
+  const uint8_t* G = gray + (size_t)frame * W * H;
+  float* out = I + (size_t)frame * W * H;
+  const int x0 = (blockIdx.x * 32 + lane) * 8;
+  const int y0 = (blockIdx.y * 8 + warp) * 4;
+  if (y0 >= H) return;                           // whole warp
+  const bool act = x0 < W;
+  float hrow[6][8];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    const int y = reflect101(y0 - 1 + r, H);
+    const uint8_t* row = G + (size_t)y * W;
+    uint2 wd = make_uint2(0u, 0u);
+    if (act) wd = __ldg(reinterpret_cast<const uint2*>(row + x0));
+    // halo bytes: left = last byte of the lane to the left, right = first byte of the lane to the right
+    unsigned left = __shfl_up_sync(0xffffffffu, wd.y >> 24, 1);
+    unsigned right = __shfl_down_sync(0xffffffffu, wd.x & 0xffu, 1);
+    if (act) {
+      if (lane == 0 || x0 == 0) left = __ldg(row + (x0 > 0 ? x0 - 1 : 1 % W));
+      if (lane == 31 || x0 + 8 >= W) right = __ldg(row + (x0 + 8 < W ? x0 + 8 : reflect101(x0 + 8, W)));
+    }
+    float g[10];
+    g[0] = (float)left;
+    g[1] = (float)(wd.x & 0xffu); g[2] = (float)((wd.x >> 8) & 0xffu); g[3] = (float)((wd.x >> 16) & 0xffu); g[4] = (float)(wd.x >> 24);
+    g[5] = (float)(wd.y & 0xffu); g[6] = (float)((wd.y >> 8) & 0xffu); g[7] = (float)((wd.y >> 16) & 0xffu); g[8] = (float)(wd.y >> 24);
+    g[9] = (float)right;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hrow[r][i] = fmaf(t2, g[i + 2], fmaf(t1, g[i + 1], t0 * g[i]));
+  }
+  if (!act) return;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int y = y0 + j;
+    if (y >= H) break;
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaf(t2, hrow[j + 2][i], fmaf(t1, hrow[j + 1][i], t0 * hrow[j][i]));
+    float4* dst = reinterpret_cast<float4*>(out + (size_t)y * W + x0);
+    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Tensor-map type and the TMA L2 prefetch, shared by updmat_init_kernel and iter15_tma_kernel.
 // A prefetch has no shared-memory destination and nothing to wait for: it only pulls one box of
@@ -1624,6 +1676,7 @@ struct stb_farneback {
   int fast_pyr;          // levels 1.. from one horizontal + one vertical launch (pyr_h_kernel / pyr_v_kernel)
   PyrTaps3 taps3;
   int init_prefetch_waves;   // updmat_init_kernel's prefetch distance in resident waves
+  int old_pyr0;              // A/B knob: the 4 x 4-patch pyr0_kernel instead of pyr0x8_kernel
   int init_minb;             // experiment knob: updmat_init_kernel's minimum blocks per SM (register cap 48 / 64 / 80)
   int band_iter, band_init;  // TileOrder.band of the iteration kernels (tile rows of 32 px) / updmat_init_kernel (rows of 8 px); 0 = round-1 order
   // device workspace
@@ -1922,6 +1975,7 @@ int stb_farneback_create(int width, int height, int max_pairs, const stb_farneba
     h->band_iter = 4;
     h->band_init = -1;
     h->init_minb = 5;
+    h->old_pyr0 = getenv("STB_OLD_PYR0") ? 1 : 0;
     if (const char* env = getenv("STB_INIT_MINB")) h->init_minb = atoi(env);
     if (const char* env = getenv("STB_BAND_ITER")) h->band_iter = atoi(env);
     if (const char* env = getenv("STB_BAND_INIT")) h->band_init = atoi(env);
@@ -2110,8 +2164,12 @@ static int prep_level(stb_farneback* h, int k, int fa, int fb, bool fastpyr, cud
     // I_k already produced by pyr_h_kernel / pyr_v_kernel
   } else if (k == 0) {
     // rows of the gray plane and of I are 4/16-byte aligned iff W % 4 == 0 (bases are 256-byte aligned)
-    stb_launch(pyr0_kernel, dim3(ceil_div(w, 128), ceil_div(hh, 32), fb - fa), dim3(256), 0, sp,
-               (const uint8_t*)h->gray, h->I, w, hh, pp.taps[0], pp.taps[1], pp.taps[2], fa, (w % 4 == 0) ? 1 : 0);
+    if ((w % 8) == 0 && !h->old_pyr0)
+      stb_launch(pyr0x8_kernel, dim3(ceil_div(w, 256), ceil_div(hh, 32), fb - fa), dim3(256), 0, sp,
+                 (const uint8_t*)h->gray, h->I, w, hh, pp.taps[0], pp.taps[1], pp.taps[2], fa);
+    else
+      stb_launch(pyr0_kernel, dim3(ceil_div(w, 128), ceil_div(hh, 32), fb - fa), dim3(256), 0, sp,
+                 (const uint8_t*)h->gray, h->I, w, hh, pp.taps[0], pp.taps[1], pp.taps[2], fa, (w % 4 == 0) ? 1 : 0);
     STB_CHECK_LAUNCH("pyr0_kernel");
   } else if (h->pow2[k]) {
     const dim3 g(ceil_div(w, 32), ceil_div(hh, k == 3 ? 8 : 16), fb - fa);

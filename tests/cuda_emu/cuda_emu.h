@@ -33,6 +33,7 @@ struct alignas(16) int4 { int x, y, z, w; };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 
 #define __global__
 #define __device__
@@ -84,6 +85,11 @@ template <class T> static inline T __shfl_sync(unsigned, T v, int src) {
 }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) {
   return cuda_emu::from_bits<T>(cuda_emu::warp_xchg_read(cuda_emu::to_bits(v), (cuda_emu::g_linear_tid & 31) ^ (unsigned)m));
+}
+template <class T> static inline T __shfl_up_sync(unsigned, T v, unsigned d) {
+  unsigned lane = cuda_emu::g_linear_tid & 31;
+  unsigned src = lane >= d ? lane - d : lane;
+  return cuda_emu::from_bits<T>(cuda_emu::warp_xchg_read(cuda_emu::to_bits(v), src));
 }
 template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned d) {
   unsigned lane = cuda_emu::g_linear_tid & 31;
