@@ -354,18 +354,29 @@ pyr_h_kernel(const uint8_t* __restrict__ gray, float* __restrict__ Hx, int W, in
   const uint8_t* row = gray + ((size_t)frame * H + y) * W;
   const int x0 = seg * 32;
   float v[48];                      // v[j] = gray[x0 - 8 + j] with REFLECT_101 at the row ends
-  if (seg > 0 && seg < nseg - 1) {
-    const uint2 a = __ldg(reinterpret_cast<const uint2*>(row + x0 - 8));
+  {
+    // The 8 bytes left of the first segment / right of the last one lie outside the row: they are not loaded
+    // but mirrored from the segment's own bytes (REFLECT_101: x = -i -> i, x = W - 1 + i -> W - 1 - i), with
+    // predicated register moves -- no divergent per-byte path (a warp of 32 consecutive (row, segment) items
+    // crosses a row end every W / 32 items, so half the warps used to execute both paths).
+    const bool first = seg == 0, last = seg == nseg - 1;
+    uint2 a = make_uint2(0u, 0u), d = make_uint2(0u, 0u);
+    if (!first) a = __ldg(reinterpret_cast<const uint2*>(row + x0 - 8));
     const uint4 b = __ldg(reinterpret_cast<const uint4*>(row + x0));
     const uint4 c = __ldg(reinterpret_cast<const uint4*>(row + x0 + 16));
-    const uint2 d = __ldg(reinterpret_cast<const uint2*>(row + x0 + 32));
+    if (!last) d = __ldg(reinterpret_cast<const uint2*>(row + x0 + 32));
     unpack4(a.x, v); unpack4(a.y, v + 4);
     unpack4(b.x, v + 8); unpack4(b.y, v + 12); unpack4(b.z, v + 16); unpack4(b.w, v + 20);
     unpack4(c.x, v + 24); unpack4(c.y, v + 28); unpack4(c.z, v + 32); unpack4(c.w, v + 36);
     unpack4(d.x, v + 40); unpack4(d.y, v + 44);
-  } else {
+    if (first) {
 #pragma unroll
-    for (int j = 0; j < 48; ++j) v[j] = (float)__ldg(row + reflect101(x0 - 8 + j, W));
+      for (int j = 0; j < 8; ++j) v[j] = v[16 - j];
+    }
+    if (last) {
+#pragma unroll
+      for (int k = 40; k < 48; ++k) v[k] = v[78 - k];
+    }
   }
   // frame-major intermediate: [frame][level-1 rows | level-2 rows | level-3 rows]
   const int w1 = W >> 1, w2 = W >> 2, w3 = W >> 3;
@@ -426,10 +437,19 @@ __device__ __forceinline__ void pyr_v_quad(const float* __restrict__ hx, float* 
   const int oy = q / qpr, ox = (q - oy * qpr) * 4;
   const int r_lo = S * oy + S / 2 - 1 - RAD;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (r_lo >= 0 && r_lo + NT - 1 < H) {          // interior rows (warp-uniform: a warp's quads share oy): no reflection
+    const float* p = hx + (size_t)r_lo * wK + ox;
 #pragma unroll
-  for (int t = 0; t < NT; ++t) {
-    const float4 h = __ldg(reinterpret_cast<const float4*>(hx + (size_t)reflect101(r_lo + t, H) * wK + ox));
-    a0 = fmaf(taps[t], h.x, a0); a1 = fmaf(taps[t], h.y, a1); a2 = fmaf(taps[t], h.z, a2); a3 = fmaf(taps[t], h.w, a3);
+    for (int t = 0; t < NT; ++t) {
+      const float4 h = __ldg(reinterpret_cast<const float4*>(p + (size_t)t * wK));
+      a0 = fmaf(taps[t], h.x, a0); a1 = fmaf(taps[t], h.y, a1); a2 = fmaf(taps[t], h.z, a2); a3 = fmaf(taps[t], h.w, a3);
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const float4 h = __ldg(reinterpret_cast<const float4*>(hx + (size_t)reflect101(r_lo + t, H) * wK + ox));
+      a0 = fmaf(taps[t], h.x, a0); a1 = fmaf(taps[t], h.y, a1); a2 = fmaf(taps[t], h.z, a2); a3 = fmaf(taps[t], h.w, a3);
+    }
   }
   *reinterpret_cast<float4*>(out + (size_t)oy * wK + ox) = make_float4(a0, a1, a2, a3);
 }
@@ -502,12 +522,33 @@ pyr0_kernel(const uint8_t* __restrict__ gray, float* __restrict__ I, int W, int 
   }
 }
 
-// Level 0 again, for W % 8 == 0: a thread owns 8 pixels x 4 rows.  Six 8-byte row loads (the 4 rows + one above
-// and below, REFLECT_101), the two horizontal halo bytes of every row come from the neighbouring lanes by shuffle
-// (lanes 0 / 31 and the image edges load them), bytes are converted to float once, the separable 3x3 runs in
-// registers in the same fmaf order as pyr0_kernel (bit-identical), four rows of two 16-byte stores.  About a
-// third of pyr0_kernel's instructions per pixel (that kernel spends them on per-byte halo loads and per-row
-// border arithmetic for a 4 x 4 patch).
+// Level 0 again, for W % 8 == 0: a thread owns an 8-pixel column strip and walks kPyr0Rows rows down it.  Per row:
+// one 8-byte load (issued one row ahead of its use), the two horizontal halo bytes from the neighbouring lanes
+// by shuffle (lanes 0 / 31 and the image edges load them), bytes converted to float once, the horizontal 3-tap
+// into a rolling three-row window in registers, the vertical 3-tap, two 16-byte stores -- the same fmaf order
+// as pyr0_kernel (bit-identical).  About a third of pyr0_kernel's instructions per pixel (that kernel spends
+// them on per-byte halo loads and per-row border arithmetic for a 4 x 4 patch) and, unlike a one-shot
+// patch-per-thread kernel (53 us against pyr0_kernel's 55 us: both latency-bound, issue 47 %, DRAM 26 %), the
+// loads of the next row are always in flight.
+constexpr int kPyr0Rows = 16;
+
+__device__ __forceinline__ void pyr0_hrow(const uint8_t* __restrict__ row, uint2 wd, int x0, int W, int lane, bool act,
+                                          float t0, float t1, float t2, float* hr) {
+  unsigned left = __shfl_up_sync(0xffffffffu, wd.y >> 24, 1);
+  unsigned right = __shfl_down_sync(0xffffffffu, wd.x & 0xffu, 1);
+  if (act) {
+    if (lane == 0 || x0 == 0) left = __ldg(row + (x0 > 0 ? x0 - 1 : 1 % W));
+    if (lane == 31 || x0 + 8 >= W) right = __ldg(row + (x0 + 8 < W ? x0 + 8 : reflect101(x0 + 8, W)));
+  }
+  float g[10];
+  g[0] = (float)left;
+  g[1] = (float)(wd.x & 0xffu); g[2] = (float)((wd.x >> 8) & 0xffu); g[3] = (float)((wd.x >> 16) & 0xffu); g[4] = (float)(wd.x >> 24);
+  g[5] = (float)(wd.y & 0xffu); g[6] = (float)((wd.y >> 8) & 0xffu); g[7] = (float)((wd.y >> 16) & 0xffu); g[8] = (float)(wd.y >> 24);
+  g[9] = (float)right;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) hr[i] = fmaf(t2, g[i + 2], fmaf(t1, g[i + 1], t0 * g[i]));
+}
+
 __global__ void __launch_bounds__(256)
 pyr0x8_kernel(const uint8_t* __restrict__ gray, float* __restrict__ I, int W, int H, float t0, float t1, float t2, int frame0) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -515,42 +556,37 @@ pyr0x8_kernel(const uint8_t* __restrict__ gray, float* __restrict__ I, int W, in
   const uint8_t* G = gray + (size_t)frame * W * H;
   float* out = I + (size_t)frame * W * H;
   const int x0 = (blockIdx.x * 32 + lane) * 8;
-  const int y0 = (blockIdx.y * 8 + warp) * 4;
-  if (y0 >= H) return;                           // whole warp
+  const int yb = (blockIdx.y * 8 + warp) * kPyr0Rows;
+  if (yb >= H) return;                           // whole warp
   const bool act = x0 < W;
-  float hrow[6][8];
-#pragma unroll
-  for (int r = 0; r < 6; ++r) {
-    const int y = reflect101(y0 - 1 + r, H);
-    const uint8_t* row = G + (size_t)y * W;
-    uint2 wd = make_uint2(0u, 0u);
-    if (act) wd = __ldg(reinterpret_cast<const uint2*>(row + x0));
-    // halo bytes: left = last byte of the lane to the left, right = first byte of the lane to the right
-    unsigned left = __shfl_up_sync(0xffffffffu, wd.y >> 24, 1);
-    unsigned right = __shfl_down_sync(0xffffffffu, wd.x & 0xffu, 1);
-    if (act) {
-      if (lane == 0 || x0 == 0) left = __ldg(row + (x0 > 0 ? x0 - 1 : 1 % W));
-      if (lane == 31 || x0 + 8 >= W) right = __ldg(row + (x0 + 8 < W ? x0 + 8 : reflect101(x0 + 8, W)));
-    }
-    float g[10];
-    g[0] = (float)left;
-    g[1] = (float)(wd.x & 0xffu); g[2] = (float)((wd.x >> 8) & 0xffu); g[3] = (float)((wd.x >> 16) & 0xffu); g[4] = (float)(wd.x >> 24);
-    g[5] = (float)(wd.y & 0xffu); g[6] = (float)((wd.y >> 8) & 0xffu); g[7] = (float)((wd.y >> 16) & 0xffu); g[8] = (float)(wd.y >> 24);
-    g[9] = (float)right;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) hrow[r][i] = fmaf(t2, g[i + 2], fmaf(t1, g[i + 1], t0 * g[i]));
+  const int yend = min(yb + kPyr0Rows, H);        // warp-uniform
+  auto row_ptr = [&](int yy) { return G + (size_t)reflect101(yy, H) * W; };
+  auto load = [&](const uint8_t* row) { return act ? __ldg(reinterpret_cast<const uint2*>(row + x0)) : make_uint2(0u, 0u); };
+  float hp[8], hc[8], hn[8];
+  {
+    const uint8_t* ra = row_ptr(yb - 1);
+    const uint8_t* rb = row_ptr(yb);
+    const uint2 wa = load(ra), wb = load(rb);
+    pyr0_hrow(ra, wa, x0, W, lane, act, t0, t1, t2, hp);
+    pyr0_hrow(rb, wb, x0, W, lane, act, t0, t1, t2, hc);
   }
-  if (!act) return;
+  const uint8_t* rn = row_ptr(yb + 1);
+  uint2 wn = load(rn);
+  for (int y = yb; y < yend; ++y) {
+    const uint8_t* rnn = row_ptr(y + 2);
+    const uint2 wnn = load(rnn);                   // in flight while this row is finished
+    pyr0_hrow(rn, wn, x0, W, lane, act, t0, t1, t2, hn);
+    if (act) {
+      float o[8];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int y = y0 + j;
-    if (y >= H) break;
-    float o[8];
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(t2, hn[i], fmaf(t1, hc[i], t0 * hp[i]));
+      float4* dst = reinterpret_cast<float4*>(out + (size_t)y * W + x0);
+      dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = fmaf(t2, hrow[j + 2][i], fmaf(t1, hrow[j + 1][i], t0 * hrow[j][i]));
-    float4* dst = reinterpret_cast<float4*>(out + (size_t)y * W + x0);
-    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    for (int i = 0; i < 8; ++i) { hp[i] = hc[i]; hc[i] = hn[i]; }
+    rn = rnn; wn = wnn;
   }
 }
 
@@ -2165,7 +2201,7 @@ static int prep_level(stb_farneback* h, int k, int fa, int fb, bool fastpyr, cud
   } else if (k == 0) {
     // rows of the gray plane and of I are 4/16-byte aligned iff W % 4 == 0 (bases are 256-byte aligned)
     if ((w % 8) == 0 && !h->old_pyr0)
-      stb_launch(pyr0x8_kernel, dim3(ceil_div(w, 256), ceil_div(hh, 32), fb - fa), dim3(256), 0, sp,
+      stb_launch(pyr0x8_kernel, dim3(ceil_div(w, 256), ceil_div(hh, 8 * kPyr0Rows), fb - fa), dim3(256), 0, sp,
                  (const uint8_t*)h->gray, h->I, w, hh, pp.taps[0], pp.taps[1], pp.taps[2], fa);
     else
       stb_launch(pyr0_kernel, dim3(ceil_div(w, 128), ceil_div(hh, 32), fb - fa), dim3(256), 0, sp,
