@@ -1544,14 +1544,16 @@ constexpr unsigned kTmStageBytes = kTmStageFloats * sizeof(float);
 __device__ __forceinline__ void tma_mbar_init(unsigned long long*, int) {}
 // the emulated copy is synchronous in thread 0: a block barrier stands in for the mbarrier wait
 __device__ __forceinline__ void tma_mbar_wait(unsigned long long*, unsigned) { __syncthreads(); }
+template <int BW = kTmRawW, int BH = kTmRawH, bool TX = true>
 __device__ __forceinline__ void tma_load_tile(float* dst, const TmaMap3D* m, int x0, int y0, int z, unsigned long long*) {
   if (x0 & 3) { fprintf(stderr, "cuda_emu: TMA inner coordinate %d is not 16-byte aligned\n", x0); abort(); }
-  for (int r = 0; r < kTmRawH; ++r)
-    for (int c = 0; c < kTmRawW; ++c) {
+  for (int r = 0; r < BH; ++r)
+    for (int c = 0; c < BW; ++c) {
       const int x = x0 + c, y = y0 + r;
-      dst[r * kTmRawW + c] = (x >= 0 && x < m->w && y >= 0 && y < m->h) ? m->base[((size_t)z * m->h + y) * m->w + x] : 0.f;
+      dst[r * BW + c] = (x >= 0 && x < m->w && y >= 0 && y < m->h) ? m->base[((size_t)z * m->h + y) * m->w + x] : 0.f;
     }
 }
+__device__ __forceinline__ void tma_mbar_arrive(unsigned long long*) {}
 #else
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tma_mbar_init(unsigned long long* bar, int count) {
@@ -1576,8 +1578,13 @@ __device__ __forceinline__ void tma_mbar_wait(unsigned long long* bar, unsigned 
   }
   __trap();
 }
+__device__ __forceinline__ void tma_mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// TX = false: the caller has already armed the barrier with the byte count of several copies
+template <int BW = kTmRawW, int BH = kTmRawH, bool TX = true>
 __device__ __forceinline__ void tma_load_tile(float* dst, const TmaMap3D* map, int x0, int y0, int z, unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(kTmStageBytes) : "memory");
+  if (TX) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"((unsigned)(BW * BH * sizeof(float))) : "memory");
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<unsigned long long>(map)), "r"(x0), "r"(y0), "r"(z), "r"(smem_u32(bar))
@@ -1690,6 +1697,242 @@ iter15_tma_kernel(const STB_GRID_CONSTANT TmaMap3D map_in, float* __restrict__ M
   iter15_global_phase<UPDATE, HIST>(fl, fh, Mout, R, flow_out, flow_hist, w, h, pair, bpz, ox0, oy0);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// The update iteration with a FLOW-COMPENSATED R1 WINDOW in shared memory.
+// In iter15_tma_kernel the update phase gathers R1 at (x + dx, y + dy) with 30 global loads per
+// pixel pair; every warp then sits on the first consumer of those loads (21 % of the kernel's stall
+// samples; no pipe above 67 %) -- the register file is full (64 x 1024 threads per SM), so more
+// loads in flight per thread are not to be had.  Here the gathers read shared memory instead:
+// after the 2x2 solve the block reduces the bounding box of floor(x + dx), floor(y + dy) over its
+// in-image pixels; if the box fits 56 x 38 (the 48 x 32 tile + 8 / 6 of slack, its origin rounded
+// down to 4 floats for TMA), one thread fetches that box of the five R1 planes with five
+// cp.async.bulk.tensor copies whose ORIGIN IS THE DATA-DEPENDENT box corner, while everybody
+// issues their (flow-independent) R0 loads; the bilinear footprints are then LDS with immediate
+// offsets off one base address.  Smooth flow -- any global motion, however large -- fits; tiles
+// that straddle a motion boundary do not and take the global-memory gathers, as do pixel pairs
+// whose footprints do not share a row.  Same arithmetic as update_matrices_vpair.
+// Shared memory: raw ring + Vt (39.9 KB, dead after the box phase) are overlaid by the staged flow
+// (12.25 KB) and the window (5 x 8.4 KB): 55.5 KB per block, still 4 blocks per SM.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWinW = 56, kWinH = 38;
+constexpr int kWinPlaneFloats = 2144;                         // 56 * 38 = 2128, rounded up to a multiple of 32 floats (128 B)
+constexpr size_t kWinFlBytes = 12544;                         // 32 x 49 float2
+constexpr size_t kWinSmemWin = kWinFlBytes;                   // window starts right after the staged flow
+constexpr size_t kWinSmemBars = kWinSmemWin + 5 * kWinPlaneFloats * sizeof(float);   // 55424
+constexpr size_t kWinSmemBytes = kWinSmemBars + 64;
+static_assert(kWinW * kWinH <= kWinPlaneFloats && (kWinFlBytes % 128) == 0 && ((kWinPlaneFloats * 4) % 128) == 0, "TMA destinations are 128-byte aligned");
+static_assert(2 * kTmStageBytes + 2 * kFiVtWords * sizeof(float) <= kWinSmemBars, "box-phase buffers fit under the barriers");
+
+__device__ __forceinline__ void um_vpair_win(const float* __restrict__ R0, const float* __restrict__ R1, const float* __restrict__ win,
+                                             int wx0, int wy0, bool fits, int n, int w, int h, int x, int y, float2 fa, float2 fb,
+                                             float ma[5], float mb[5]) {
+  const int o = y * w + x;
+  float qa[5], qb[5];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) { qa[c] = __ldg(R0 + c * n + o); qb[c] = __ldg(R0 + c * n + o + w); }
+  float fxa = (float)x + fa.x, fya = (float)y + fa.y;
+  float fxb = (float)x + fb.x, fyb = (float)(y + 1) + fb.y;
+  const int x1a = __float2int_rd(fxa), y1a = __float2int_rd(fya);
+  const int x1b = __float2int_rd(fxb), y1b = __float2int_rd(fyb);
+  const bool ina = (unsigned)x1a < (unsigned)(w - 1) && (unsigned)y1a < (unsigned)(h - 1);
+  const bool inb = (unsigned)x1b < (unsigned)(w - 1) && (unsigned)y1b < (unsigned)(h - 1);
+  if (ina && inb && x1b == x1a && y1b == y1a + 1) {
+    fxa -= (float)x1a; fya -= (float)y1a; fxb -= (float)x1b; fyb -= (float)y1b;
+    const float a00 = (1.f - fxa) * (1.f - fya), a01 = fxa * (1.f - fya), a10 = (1.f - fxa) * fya, a11 = fxa * fya;
+    const float b00 = (1.f - fxb) * (1.f - fyb), b01 = fxb * (1.f - fyb), b10 = (1.f - fxb) * fyb, b11 = fxb * fyb;
+    float ra[5], rb[5];
+    if (fits) {
+      const float* p = win + (y1a - wy0) * kWinW + (x1a - wx0);
+#pragma unroll
+      for (int pl = 0; pl < 5; ++pl) {
+        const float t00 = p[pl * kWinPlaneFloats], t01 = p[pl * kWinPlaneFloats + 1];
+        const float t10 = p[pl * kWinPlaneFloats + kWinW], t11 = p[pl * kWinPlaneFloats + kWinW + 1];
+        const float t20 = p[pl * kWinPlaneFloats + 2 * kWinW], t21 = p[pl * kWinPlaneFloats + 2 * kWinW + 1];
+        ra[pl] = a00 * t00 + a01 * t01 + a10 * t10 + a11 * t11;
+        rb[pl] = b00 * t10 + b01 * t11 + b10 * t20 + b11 * t21;
+      }
+    } else {
+      const float* p = R1 + (y1a * w + x1a);
+#pragma unroll
+      for (int pl = 0; pl < 5; ++pl) {
+        const float t00 = __ldg(p + pl * n), t01 = __ldg(p + pl * n + 1);
+        const float t10 = __ldg(p + pl * n + w), t11 = __ldg(p + pl * n + w + 1);
+        const float t20 = __ldg(p + pl * n + 2 * w), t21 = __ldg(p + pl * n + 2 * w + 1);
+        ra[pl] = a00 * t00 + a01 * t01 + a10 * t10 + a11 * t11;
+        rb[pl] = b00 * t10 + b01 * t11 + b10 * t20 + b11 * t21;
+      }
+    }
+    um_finish(qa[0], qa[1], qa[2], qa[3], qa[4], true, ra[0], ra[1], ra[2], ra[3], ra[4], w, h, x, y, fa.x, fa.y, ma);
+    um_finish(qb[0], qb[1], qb[2], qb[3], qb[4], true, rb[0], rb[1], rb[2], rb[3], rb[4], w, h, x, y + 1, fb.x, fb.y, mb);
+  } else {
+    update_matrices_q(qa[0], qa[1], qa[2], qa[3], qa[4], R1, n, w, h, x, y, fa.x, fa.y, ma);
+    update_matrices_q(qb[0], qb[1], qb[2], qb[3], qb[4], R1, n, w, h, x, y + 1, fb.x, fb.y, mb);
+  }
+}
+
+__global__ void __launch_bounds__(kFiThreads, 4)
+iter15_win_kernel(const STB_GRID_CONSTANT TmaMap3D map_in, float* __restrict__ Mout, const float* __restrict__ R,
+                  int w, int h, int pair0, const STB_GRID_CONSTANT TmaMap3D map_R, int prefetch_R,
+                  const STB_GRID_CONSTANT TmaMap3D map_Rw, TileOrder ord) {
+#ifdef STB_CPU_EMU
+  unsigned char* smem = cuda_emu::dyn_smem();
+#else
+  extern __shared__ __align__(128) unsigned char smem[];
+#endif
+  float (*raw)[kTmStageFloats] = reinterpret_cast<float (*)[kTmStageFloats]>(smem);                       // box phase
+  float (*Vt)[kFiVtWords] = reinterpret_cast<float (*)[kFiVtWords]>(smem + 2 * kTmStageBytes);            // box phase
+  float2* fl = reinterpret_cast<float2*>(smem);                                                            // update phase
+  float* win = reinterpret_cast<float*>(smem + kWinSmemWin);                                               // update phase
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + kWinSmemBars);                   // [0,1] M ring, [2] window
+  int* wprm = reinterpret_cast<int*>(smem + kWinSmemBars + 24);                                            // wx0, wy0, fits
+  __shared__ int s_wbox[8][4];                                                                             // per-warp footprint boxes
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int btx, bty, bpz;
+  int bid;
+  tile_of_block(ord, btx, bty, bpz, bid);
+  const int pair = pair0 + bpz;
+  const int ox0 = btx * kFiTW, oy0 = bty * kFiTH;
+  const int bx0 = ox0 - kFiM - 1, by0 = oy0 - kFiM;
+
+  if (tid == 0) {
+    tma_mbar_init(&bars[0], 1);
+    tma_mbar_init(&bars[1], 1);
+    tma_mbar_init(&bars[2], 1);
+#ifndef STB_CPU_EMU
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+  }
+  __syncthreads();
+  if (tid == 0) {
+    tma_load_tile(raw[0], &map_in, bx0, by0, pair * 5 + 0, &bars[0]);
+    tma_load_tile(raw[1], &map_in, bx0, by0, pair * 5 + 1, &bars[1]);
+  }
+  if (prefetch_R && tid >= 32 && tid < ((ord.band == 0 || ord.band == -2 || bpz == ord.np - 1) ? 42 : 37))
+    tma_prefetch_l2(&map_R, ox0, oy0, pair * 5 + (tid - 32));
+
+  // ---- box phase: identical to iter15_tma_kernel
+  const int vg = tid >> 6, vcx = tid & 63;
+  const bool vact = vcx < kFiRawW;
+  const bool border = (bx0 + 1 < 0) || (by0 < 0) || (bx0 + 1 + kFiRawW > w) || (by0 + kTmRawH > h);
+  const int ccol = min(max(bx0 + 1 + vcx, 0), w - 1) - bx0;
+  float sums[5][kFiGC];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    const int st = c & 1;
+    tma_mbar_wait(&bars[st], (unsigned)((c >> 1) & 1));
+    float* vt = Vt[st];
+    if (vact) {
+      float v[kFiRows];
+      if (!border) {
+        const float* col = &raw[st][(vg * 8) * kTmRawW + vcx + 1];
+#pragma unroll
+        for (int j = 0; j < kFiRows; ++j) v[j] = col[j * kTmRawW];
+      } else {
+#pragma unroll
+        for (int j = 0; j < kFiRows; ++j) {
+          const int rr = min(max(by0 + vg * 8 + j, 0), h - 1) - by0;
+          v[j] = raw[st][rr * kTmRawW + ccol];
+        }
+      }
+      float vs[8];
+      box15<8>(v, vs);
+      float* o = vt + vcx * 33 + vg * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = vs[i];
+    }
+    __syncthreads();
+    if (tid == 0 && c + 2 < 5) tma_load_tile(raw[st], &map_in, bx0, by0, pair * 5 + c + 2, &bars[st]);
+    {
+      const float* rowp = vt + (warp * kFiGC) * 33 + lane;
+      float t[kFiGC + 14];
+#pragma unroll
+      for (int j = 0; j < kFiGC + 14; ++j) t[j] = rowp[j * 33];
+      box15<kFiGC>(t, sums[c]);
+    }
+  }
+  __syncthreads();   // every read of raw / Vt is done before fl and the window overlay them
+
+  // ---- solve + bounding box of the bilinear footprints of this thread's pixels (row oy0 + lane, columns ox0 + 6 warp ..)
+  int minx = 0x7fffffff, miny = 0x7fffffff, maxx = -1, maxy = -1;
+  {
+    const int y = oy0 + lane;
+#pragma unroll
+    for (int i = 0; i < kFiGC; ++i) {
+      const float2 f = solve_flow15(sums[0][i], sums[1][i], sums[2][i], sums[3][i], sums[4][i]);
+      fl[lane * kFiFlStride + warp * kFiGC + i] = f;
+      const int x = ox0 + warp * kFiGC + i;
+      if (x < w && y < h) {
+        const int x1 = __float2int_rd((float)x + f.x), y1 = __float2int_rd((float)y + f.y);
+        if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
+          minx = min(minx, x1); maxx = max(maxx, x1 + 1);
+          miny = min(miny, y1); maxy = max(maxy, y1 + 1);
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      minx = min(minx, __shfl_xor_sync(0xffffffffu, minx, d)); maxx = max(maxx, __shfl_xor_sync(0xffffffffu, maxx, d));
+      miny = min(miny, __shfl_xor_sync(0xffffffffu, miny, d)); maxy = max(maxy, __shfl_xor_sync(0xffffffffu, maxy, d));
+    }
+  }
+  if (lane == 0) { s_wbox[warp][0] = minx; s_wbox[warp][1] = maxx; s_wbox[warp][2] = miny; s_wbox[warp][3] = maxy; }
+  __syncthreads();   // staged flow + warp boxes visible
+  if (tid == 0) {
+    int bx_lo = 0x7fffffff, bx_hi = -1, by_lo = 0x7fffffff, by_hi = -1;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      bx_lo = min(bx_lo, s_wbox[q][0]); bx_hi = max(bx_hi, s_wbox[q][1]);
+      by_lo = min(by_lo, s_wbox[q][2]); by_hi = max(by_hi, s_wbox[q][3]);
+    }
+    const int wx0 = bx_lo & ~3, wy0 = by_lo;
+    const int fits = (bx_hi >= 0) && (bx_hi - wx0 < kWinW) && (by_hi - wy0 < kWinH);
+    wprm[0] = wx0; wprm[1] = wy0; wprm[2] = fits;
+    if (fits) {
+#ifndef STB_CPU_EMU
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bars[2])),
+                   "r"((unsigned)(5 * kWinW * kWinH * sizeof(float))) : "memory");
+#endif
+#pragma unroll
+      for (int c = 0; c < 5; ++c)
+        tma_load_tile<kWinW, kWinH, false>(win + c * kWinPlaneFloats, &map_Rw, wx0, wy0, (pair + 1) * 5 + c, &bars[2]);
+    } else {
+      tma_mbar_arrive(&bars[2]);      // nothing to wait for: release the parameters
+    }
+  }
+
+  // ---- update phase: vertical pixel pairs, consecutive lanes on consecutive x
+  const size_t n = (size_t)w * h;
+  const int ni = (int)n;
+  const float* R0 = R + (size_t)pair * 5 * n;
+  const float* R1 = R0 + 5 * n;
+  float* Mp = Mout + (size_t)pair * 5 * n;
+  tma_mbar_wait(&bars[2], 0u);
+  const int wx0 = wprm[0], wy0 = wprm[1];
+  const bool fits = wprm[2] != 0;
+#pragma unroll 1
+  for (int i = 0; i < (kFiTW * kFiTH) / (2 * kFiThreads); ++i) {
+    const int p2 = tid + i * kFiThreads;
+    const int tp = p2 / kFiTW, tx = p2 - tp * kFiTW;
+    const int x = ox0 + tx, y = oy0 + 2 * tp;
+    if (x >= w || y >= h) continue;
+    const float2 fa = fl[(2 * tp) * kFiFlStride + tx];
+    const float2 fb = fl[(2 * tp + 1) * kFiFlStride + tx];
+    float* Mo = Mp + (y * w + x);
+    float ma[5], mb[5];
+    if (y + 1 < h) {
+      um_vpair_win(R0, R1, win, wx0, wy0, fits, ni, w, h, x, y, fa, fb, ma, mb);
+#pragma unroll
+      for (int c = 0; c < 5; ++c) { Mo[c * ni] = ma[c]; Mo[c * ni + w] = mb[c]; }
+    } else {
+      update_matrices_px(R0, R1, ni, w, h, x, y, fa.x, fa.y, ma);
+#pragma unroll
+      for (int c = 0; c < 5; ++c) Mo[c * ni] = ma[c];
+    }
+  }
+}
+
 }  // namespace stb
 
 // =============================================================================================
@@ -1741,6 +1984,8 @@ struct stb_farneback {
   // R at every level ([5*F planes][h_k][w_k]) for the L2 prefetch of the update phase's tiles
   TmaMap3D tmapR[kMaxScales];
   int prefetch_R[kMaxScales];
+  TmaMap3D tmapRw[kMaxScales];   // same tensor, 56 x 38 boxes: iter15_win_kernel's flow-compensated R1 window
+  int use_win[kMaxScales];
   TmaMap3D tmapRi[kMaxScales];   // same tensor, 64 x 8 boxes: updmat_init_kernel's prefetch-ahead
   int prefetch_Ri[kMaxScales];
   // measurement hook: event pairs around the level-0 update-iteration kernels
@@ -2066,6 +2311,9 @@ int stb_farneback_create(int width, int height, int max_pairs, const stb_farneba
       if (h->use_tma[k] && !getenv("STB_NO_R_PREFETCH") && h->h[k] >= kPfBoxH &&
           make_tmap(&h->tmapR[k], h->Rk[k], h->w[k], h->h[k], 5 * (max_pairs + 1), kPfBoxW, kPfBoxH))
         h->prefetch_R[k] = 1;
+      if (h->use_tma[k] && h->prefetch_R[k] && !getenv("STB_NO_WIN") && h->w[k] >= kWinW && h->h[k] >= kWinH &&
+          make_tmap(&h->tmapRw[k], h->Rk[k], h->w[k], h->h[k], 5 * (max_pairs + 1), kWinW, kWinH))
+        h->use_win[k] = 1;
       if (!(no_tma && no_tma[0] == '1') && !getenv("STB_NO_INIT_PREFETCH") &&
           make_tmap(&h->tmapRi[k], h->Rk[k], h->w[k], h->h[k], 5 * (max_pairs + 1), 64, kPfInitBoxH))
         h->prefetch_Ri[k] = 1;
@@ -2081,6 +2329,8 @@ int stb_farneback_create(int width, int height, int max_pairs, const stb_farneba
     e = cudaFuncSetAttribute(iter_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iter_smem_bytes(kItMaxHalo));
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(pyr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(iter15_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinSmemBytes);
   if (e != cudaSuccess) {
     cudaFree(base);
     delete h;
@@ -2339,7 +2589,10 @@ static int run_levels(stb_farneback* h, int n, float* const* d_flow, cudaStream_
       for (int it = 0; it < h->prm.num_iters; ++it) {
         if (it < h->prm.num_iters - 1) {
           if (prof && it == 0) { int prc = prof_mark(h, s); if (prc) return prc; }
-          if (fast15 && h->use_tma[k])
+          if (fast15 && h->use_tma[k] && h->use_win[k])
+            stb_launch(iter15_win_kernel, grid, dim3(kFiThreads), kWinSmemBytes, s, h->tmap[mc][k], h->M[mc ^ 1],
+                       Rk, w, hh, p0, h->tmapR[k], h->prefetch_R[k], h->tmapRw[k], ot);
+          else if (fast15 && h->use_tma[k])
             stb_launch(iter15_tma_kernel<true, false>, grid, dim3(kFiThreads), 0, s, h->tmap[mc][k], h->M[mc ^ 1],
                        Rk, fo, (int32_t*)nullptr, w, hh, p0, h->tmapR[k], h->prefetch_R[k], ot);
           else if (fast15)

@@ -306,3 +306,28 @@ def test_emu_border_tiles_ragged_sizes_and_fused_histogram(emu, h, w):
         assert np.array_equal(fh[i].reshape(2, 64), restate.flow_histogram(flows[i])), i
         assert np.array_equal(plain[i], flows[i])
     assert np.array_equal(fh_only, fh)
+
+
+@pytest.mark.parametrize('h,w,gen', [(120, 160, 'textured'), (97, 164, 'warped'), (76, 112, 'noise')])
+def test_emu_flow_compensated_window_equals_global_gathers(emu, h, w, gen):
+    """iter15_win_kernel stages the displaced R1 footprints of a tile in shared memory when their bounding box
+    fits (smooth motion) and falls back to global gathers per tile when it does not (noise: incoherent flow);
+    either way the flow must equal the plain iter15_tma_kernel path (STB_NO_WIN) bit for bit."""
+    clip = {'textured': lambda: synth.textured_clip(5, 3, h, w), 'warped': lambda: synth.warped_clip(6, 3, h, w),
+            'noise': lambda: synth.noise_clip(7, 3, h, w)}[gen]()
+    ft = _lib.ptr_table([f.ctypes.data for f in clip])
+    res = []
+    for no_win in (False, True):
+        if no_win:
+            os.environ['STB_NO_WIN'] = '1'
+        try:
+            hd = C.c_void_p()
+            assert emu.stb_farneback_create(w, h, 2, None, C.byref(hd)) == 0
+        finally:
+            os.environ.pop('STB_NO_WIN', None)
+        flows = [np.zeros((h, w, 2), np.float32) for _ in range(2)]
+        assert emu.stb_farneback_run(hd, ft, 2, _lib.ptr_table([f.ctypes.data for f in flows]), None) == 0, emu.stb_last_error()
+        emu.stb_farneback_destroy(hd)
+        res.append(flows)
+    for i in range(2):
+        assert np.array_equal(res[0][i], res[1][i]), i

@@ -623,3 +623,24 @@ def test_cuda_graph_replay_equals_direct_launches(torch, ops):
             graphed.execute(fr, out=out)
             assert torch.equal(out, a_flow), (rep, i)
     direct.close(); graphed.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('h,w,gen', [(480, 640, 'textured'), (1080, 1920, 'warped'), (270, 480, 'noise')])
+def test_flow_compensated_window_equals_global_gathers(torch, ops, h, w, gen):
+    """iter15_win_kernel (R1 footprints of a tile staged in shared memory by TMA at a data-dependent origin)
+    against iter15_tma_kernel (global gathers, STB_NO_WIN): bit-identical flow and fused histogram on smooth
+    motion (tiles fit), blob borders (some tiles do not) and noise (incoherent flow: most tiles fall back)."""
+    clip = {'textured': lambda: synth.textured_clip(5, 4, h, w), 'warped': lambda: synth.warped_clip(6, 4, h, w),
+            'noise': lambda: synth.noise_clip(7, 4, h, w)}[gen]()
+    fr = dev(torch, clip)
+    os.environ['STB_NO_WIN'] = '1'
+    try:
+        plain = ops.OpticalFlow(w, h, max_batch=3)
+    finally:
+        del os.environ['STB_NO_WIN']
+    win = ops.OpticalFlow(w, h, max_batch=3)
+    a_flow, a_fh = plain.execute_with_histogram(fr)
+    b_flow, b_fh = win.execute_with_histogram(fr)
+    assert torch.equal(a_flow, b_flow) and torch.equal(a_fh, b_fh)
+    plain.close(); win.close()
