@@ -1335,6 +1335,7 @@ __device__ __forceinline__ void box15(const float* t /* NOUT+14 */, float* out /
 }
 
 constexpr int kFiTW = 48, kFiTH = 32, kFiThreads = 256, kFiM = 7;
+constexpr int kFiHistStride = 2 * 65;   // fused FlowHistogram: per-warp table of 64 + 1 trash + 64 + 1 trash counters
 constexpr int kFiRawW = kFiTW + 2 * kFiM;     // 62
 constexpr int kFiRows = 8 + 2 * kFiM;         // 22 input rows per vertical item
 constexpr int kFiGC = 6;                      // output columns per horizontal item
@@ -1402,15 +1403,17 @@ __device__ __forceinline__ void iter15_global_phase(const float2* fl, unsigned* 
     }
     if (HIST) {
       // fused FlowHistogram (flow_histogram_kernel_cpu.cpp:33-49) of the flow just produced
-      unsigned* my = fh + warp * STB_FLOWHIST_INTS;
+      // per-warp rows: 64 magnitude bins, trash, 64 angle bins, trash -- dropped values are clamped onto the
+      // trash entries so the updates need no predicate (see flow_hist_kernel)
+      unsigned* my = fh + warp * kFiHistStride;
       int bm, ba;
       flow_bins_fast(fa.x, fa.y, bm, ba);
-      if (bm >= 0) atomicAdd(my + bm, 1u);
-      if (ba >= 0) atomicAdd(my + 64 + ba, 1u);
+      atomicAdd(my + min((unsigned)bm, 64u), 1u);
+      atomicAdd(my + 65 + min((unsigned)ba, 64u), 1u);
       if (two) {
         flow_bins_fast(fb.x, fb.y, bm, ba);
-        if (bm >= 0) atomicAdd(my + bm, 1u);
-        if (ba >= 0) atomicAdd(my + 64 + ba, 1u);
+        atomicAdd(my + min((unsigned)bm, 64u), 1u);
+        atomicAdd(my + 65 + min((unsigned)ba, 64u), 1u);
       }
     }
   }
@@ -1419,7 +1422,7 @@ __device__ __forceinline__ void iter15_global_phase(const float2* fl, unsigned* 
     if (tid < STB_FLOWHIST_INTS) {
       unsigned sum = 0;
 #pragma unroll
-      for (int wq = 0; wq < kFiThreads / 32; ++wq) sum += fh[wq * STB_FLOWHIST_INTS + tid];
+      for (int wq = 0; wq < kFiThreads / 32; ++wq) sum += fh[wq * kFiHistStride + tid + (tid >> 6)];
       if (sum) atomicAdd(flow_hist + (size_t)pair * STB_FLOWHIST_INTS + tid, (int)sum);
     }
   }
@@ -1453,9 +1456,9 @@ iter15_kernel(const float* __restrict__ Min, float* __restrict__ Mout, const flo
               PtrBatch<float> flow_out, int32_t* __restrict__ flow_hist, int w, int h, int pair0, TileOrder ord) {
   __shared__ float Vt[2][kFiVtWords];
   __shared__ float2 fl[kFiTH * kFiFlStride];
-  __shared__ unsigned fh[HIST ? (kFiThreads / 32) * STB_FLOWHIST_INTS : 1];   // warp-private 128-bin tables
+  __shared__ unsigned fh[HIST ? (kFiThreads / 32) * kFiHistStride : 1];   // warp-private 128-bin tables
   if (HIST) {
-    for (int i = threadIdx.x; i < (kFiThreads / 32) * STB_FLOWHIST_INTS; i += kFiThreads) fh[i] = 0u;
+    for (int i = threadIdx.x; i < (kFiThreads / 32) * kFiHistStride; i += kFiThreads) fh[i] = 0u;
   }
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1600,7 +1603,7 @@ iter15_tma_kernel(const STB_GRID_CONSTANT TmaMap3D map_in, float* __restrict__ M
   __shared__ __align__(128) float raw[2][kTmStageFloats];     // also reused for the staged flow after the box phase
   __shared__ float Vt[2][kFiVtWords];
   __shared__ __align__(8) unsigned long long bars[2];
-  __shared__ unsigned fh[HIST ? (kFiThreads / 32) * STB_FLOWHIST_INTS : 1];
+  __shared__ unsigned fh[HIST ? (kFiThreads / 32) * kFiHistStride : 1];
   float2* fl = reinterpret_cast<float2*>(&raw[0][0]);       // 32 x 49 float2 = 12544 B <= one stage + part of the next
   static_assert(kFiTH * kFiFlStride * sizeof(float2) <= 2 * kTmStageBytes, "staged flow must fit in the raw ring");
   static_assert(kFiRawW + 1 <= kTmRawW && (kFiTW % 4) == 0, "box covers the halo'd tile from an aligned origin");
@@ -1616,7 +1619,7 @@ iter15_tma_kernel(const STB_GRID_CONSTANT TmaMap3D map_in, float* __restrict__ M
   const int bx0 = ox0 - kFiM - 1, by0 = oy0 - kFiM;
 
   if (HIST) {
-    for (int i = tid; i < (kFiThreads / 32) * STB_FLOWHIST_INTS; i += kFiThreads) fh[i] = 0u;
+    for (int i = tid; i < (kFiThreads / 32) * kFiHistStride; i += kFiThreads) fh[i] = 0u;
   }
   if (tid == 0) {
     tma_mbar_init(&bars[0], 1);

@@ -188,10 +188,11 @@ shot_scores_kernel(const int32_t* __restrict__ hist, int n, const int32_t* __res
 // FlowHistogram: 64-bin magnitude [0,64) + 64-bin angle [0,360) of an HxWx2 f32 flow field.
 // Arithmetic reproduces OpenCV's cartToPolar (polynomial fastAtan, angleInDegrees) and
 // calcHist's double-precision bin index bit-for-bit.
-// Per-lane private 16-bit counters packed two per word: [table][64 words][lane], one table per four warps
-// (bank == lane, so a warp's updates never conflict whatever the content; two warps only collide when they hit
-// the same (bin, lane) word in the same cycle).  Round 1 kept one table per warp (64 KB, 3 blocks per SM, 34 %
-// occupancy, 0.32-0.35 of HBM, latency-bound); 16 KB per block lets six blocks be resident.
+// Per-lane private u32 counters, ONE table per block: [128 bins][32 lanes] (bank == lane, so a warp's
+// update never conflicts whatever the content; updates of different warps are different instructions
+// and serialise in the atomic unit anyway).  One update = LEA (base + bin * 128) + predicated RED.
+// History: one packed-16-bit table per warp (64 KB, 3 blocks / SM, 0.32 of HBM) -> one per 4 warps
+// (0.35) -> this form, with the ~11-instruction packed-counter update gone.
 // -------------------------------------------------------------------------------------------
 struct PtrAddrF32 {
   PtrBatch<const float> t;
@@ -206,18 +207,34 @@ struct StrideAddrF32 {
 };
 
 constexpr int kFlowHistThreads = 256;
-constexpr int kFlowHistWarps = kFlowHistThreads / 32;
-constexpr int kFlowHistWarpsPerTable = 4;
-constexpr int kFlowHistTables = kFlowHistWarps / kFlowHistWarpsPerTable;
-constexpr int kFlowHistSmemWords = kFlowHistTables * 64 * 32;  // 16 KB
+// rows: 64 magnitude bins, one trash row, 64 angle bins, one trash row.  A dropped value (bin outside 0..63)
+// is clamped onto the trash row, so the update needs no predicate: ptxas turns a predicated shared RED into
+// a BSSY / BRA / BSYNC region (+4 instructions per update).
+constexpr int kFlowHistRows = 2 * 65;
+constexpr int kFlowHistSmemWords = kFlowHistRows * 32;        // 16.25 KB
 constexpr int kFlowHistBlocksPerSM = 6;
-constexpr unsigned kFlowHistMaxPxPerThread = 8192;            // x 4 warps per table: 16-bit counters cannot overflow
 
-__device__ __forceinline__ void flow_count(unsigned* my, float x, float y) {
+#ifdef STB_CPU_EMU
+typedef unsigned* flow_tab_t;
+__device__ __forceinline__ flow_tab_t flow_tab(unsigned* sh, unsigned lane) { return sh + lane; }
+__device__ __forceinline__ void flow_inc(flow_tab_t my, int bin, int plane) {
+  atomicAdd(my + (plane * 65 + min((unsigned)bin, 64u)) * 32, 1u);
+}
+#else
+typedef unsigned flow_tab_t;                                  // 32-bit address in the shared window
+__device__ __forceinline__ flow_tab_t flow_tab(unsigned* sh, unsigned lane) {
+  return (unsigned)__cvta_generic_to_shared(sh) + lane * 4u;
+}
+__device__ __forceinline__ void flow_inc(flow_tab_t my, int bin, int plane) {
+  asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(my + (unsigned)plane * (65u * 128u) + (min((unsigned)bin, 64u) << 7)) : "memory");
+}
+#endif
+
+__device__ __forceinline__ void flow_count(flow_tab_t my, float x, float y) {
   int bm, ba;
   flow_bins_fast(x, y, bm, ba);
-  if (bm >= 0) atomicAdd(my + (bm >> 1) * 32, 1u << ((bm & 1) * 16));
-  if (ba >= 0) atomicAdd(my + (32 + (ba >> 1)) * 32, 1u << ((ba & 1) * 16));
+  flow_inc(my, bm, 0);
+  flow_inc(my, ba, 1);
 }
 
 template <class Addr>
@@ -227,14 +244,14 @@ flow_hist_kernel(Addr addr, unsigned long long npx, int32_t* __restrict__ out, u
   unsigned frame, part, nparts;
   flat_grid_decode(blockIdx.x, base_blocks, rem, frame, part, nparts);
   STB_DYN_SMEM(unsigned, sh);
-  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const unsigned tid = threadIdx.x, lane = tid & 31u;
   {
     uint4* z = reinterpret_cast<uint4*>(sh);
     for (unsigned i = tid; i < kFlowHistSmemWords / 4; i += kFlowHistThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();
   const float* f = addr(frame);
-  unsigned* my = sh + (warp / kFlowHistWarpsPerTable) * (64 * 32) + lane;
+  const flow_tab_t my = flow_tab(sh, lane);
   const unsigned long long gt = (unsigned long long)part * kFlowHistThreads + tid;
   const unsigned long long T = (unsigned long long)nparts * kFlowHistThreads;
   if ((reinterpret_cast<uintptr_t>(f) & 15u) == 0) {
@@ -259,19 +276,14 @@ flow_hist_kernel(Addr addr, unsigned long long npx, int32_t* __restrict__ out, u
     for (unsigned long long i = gt; i < npx; i += T) flow_count(my, __ldg(f + 2 * i), __ldg(f + 2 * i + 1));
   }
   __syncthreads();
-  // reduce: 2 threads per bin, each sums 16 lanes x 8 warps of its 16-bit half
+  // reduce: 2 threads per bin, each sums 16 lanes
   const unsigned bin = tid >> 1, rpart = tid & 1u;
-  const unsigned word = (bin < 64 ? (bin >> 1) : 32 + ((bin - 64) >> 1));
-  const unsigned shift = (bin & 1u) * 16u;
+  const unsigned* row = sh + (bin + (bin >> 6)) * 32 + rpart * 16;   // skip the magnitude trash row
   unsigned s = 0;
 #pragma unroll
-  for (int w = 0; w < kFlowHistTables; ++w) {
-    const unsigned* row = sh + (w * 64 + word) * 32 + rpart * 16;
-#pragma unroll
-    for (int l = 0; l < 16; l += 4) {
-      const uint4 q = *reinterpret_cast<const uint4*>(row + l);
-      s += ((q.x >> shift) & 0xffffu) + ((q.y >> shift) & 0xffffu) + ((q.z >> shift) & 0xffffu) + ((q.w >> shift) & 0xffffu);
-    }
+  for (int l = 0; l < 16; l += 4) {
+    const uint4 q = *reinterpret_cast<const uint4*>(row + l);
+    s += q.x + q.y + q.z + q.w;
   }
   s += __shfl_xor_sync(0xffffffffu, s, 1);
   if (rpart == 0 && s != 0) atomicAdd(out + (size_t)frame * STB_FLOWHIST_INTS + bin, (int)s);
@@ -366,11 +378,8 @@ static int launch_flow_hist(Addr addr, int n, unsigned long long npx, int32_t* d
   }
   const int wave = num_sms() * kFlowHistBlocksPerSM;
   const long long max_useful = (long long)((npx / 2 + (unsigned long long)kFlowHistThreads * 2 - 1) / ((unsigned long long)kFlowHistThreads * 2));
-  const long long min_needed = (long long)((npx + (unsigned long long)kFlowHistThreads * kFlowHistMaxPxPerThread - 1) /
-                                           ((unsigned long long)kFlowHistThreads * kFlowHistMaxPxPerThread));
   long long total = wave;                       // one resident wave, split unevenly over the frames
   if (max_useful >= 1 && total > max_useful * n) total = max_useful * n;
-  if (total < min_needed * n) total = min_needed * n;   // 16-bit counters: bounded pixels per thread
   if (total < n) total = n;
   const unsigned base_blocks = (unsigned)(total / n), rem = (unsigned)(total % n);
   stb_launch(flow_hist_kernel<Addr>, dim3((unsigned)total), dim3(kFlowHistThreads), kFlowHistSmemWords * sizeof(unsigned), s,

@@ -135,6 +135,8 @@ static inline float __fsqrt_rn(float a) { return std::sqrt(a); }
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 static inline int __float2int_rd(float a) { return (int)std::floor(a); }
 static inline int __float2int_rn(float a) { return (int)std::nearbyint(a); }
+static inline int __float_as_int(float a) { int r; std::memcpy(&r, &a, 4); return r; }
+static inline float __int_as_float(int a) { float r; std::memcpy(&r, &a, 4); return r; }
 static inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline int __double2int_rd(double a) { return (int)std::floor(a); }
@@ -147,6 +149,7 @@ static inline unsigned __vsub4(unsigned a, unsigned b) {
 }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
+static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
 
 // ---- runtime API subset ------------------------------------------------------------------
 typedef int cudaError_t;
