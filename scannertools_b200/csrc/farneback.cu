@@ -851,6 +851,20 @@ polyexp_generic_kernel(const float* __restrict__ I, size_t i_stride, float* __re
 // ---------------------------------------------------------------------------------------------
 // UpdateMatrices for one pixel (Appendix A.5).  R0, R1: planar 5 x n.
 // ---------------------------------------------------------------------------------------------
+// p + elems floats as ONE instruction (IMAD.WIDE).  Written as pointer + int, nvcc forms the plane / row
+// addresses of the R0 loads and M' stores of the update kernels from 64-bit IADD3 / IADD3.X / LEA / LEA.HI.X
+// chains: 36 address instructions for 10 loads (ncu source view, round 2).
+#ifdef STB_CPU_EMU
+template <class T> __device__ __forceinline__ T* padd(T* p, int elems) { return p + elems; }
+#else
+template <class T> __device__ __forceinline__ T* padd(T* p, int elems) {
+  static_assert(sizeof(T) == 4, "4-byte elements");
+  T* r;
+  asm("mad.wide.s32 %0, %1, 4, %2;" : "=l"(r) : "r"(elems), "l"(p));
+  return r;
+}
+#endif
+
 __device__ __forceinline__ float border_w(int d) { return d < 2 ? 0.14f : 0.4472f; }
 
 // second half of UpdateMatrices: from R0's planes q0..q4 at (x, y) and the (interpolated) R1
@@ -896,10 +910,13 @@ __device__ __forceinline__ void update_matrices_q(float q0, float q1, float q2, 
   const bool inside = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
   if (inside) {
     const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-    const float* p = R1 + (y1 * w + x1);
+    const float* p = padd(R1, y1 * w + x1);
 #pragma unroll
-    for (int pl = 0; pl < 5; ++pl)
-      r[pl] = a00 * __ldg(p + pl * n) + a01 * __ldg(p + pl * n + 1) + a10 * __ldg(p + pl * n + w) + a11 * __ldg(p + pl * n + w + 1);
+    for (int pl = 0; pl < 5; ++pl) {
+      const float* pw = padd(p, w);
+      r[pl] = a00 * __ldg(p) + a01 * __ldg(p + 1) + a10 * __ldg(pw) + a11 * __ldg(pw + 1);
+      p = padd(p, n);
+    }
   }
   um_finish(q0, q1, q2, q3, q4, inside, r[0], r[1], r[2], r[3], r[4], w, h, x, y, dx, dy, m);
 }
@@ -920,14 +937,16 @@ __device__ __forceinline__ void update_matrices_pair(const float2 q[5], const fl
     fxa -= (float)x1a; fya -= (float)y1a; fxb -= (float)x1b; fyb -= (float)y1b;
     const float a00 = (1.f - fxa) * (1.f - fya), a01 = fxa * (1.f - fya), a10 = (1.f - fxa) * fya, a11 = fxa * fya;
     const float b00 = (1.f - fxb) * (1.f - fyb), b01 = fxb * (1.f - fyb), b10 = (1.f - fxb) * fyb, b11 = fxb * fyb;
-    const float* p = R1 + (y1a * w + x1a);
+    const float* p = padd(R1, y1a * w + x1a);
     float ra[5], rb[5];
 #pragma unroll
     for (int pl = 0; pl < 5; ++pl) {
-      const float t0 = __ldg(p + pl * n), t1 = __ldg(p + pl * n + 1), t2 = __ldg(p + pl * n + 2);
-      const float u0 = __ldg(p + pl * n + w), u1 = __ldg(p + pl * n + w + 1), u2 = __ldg(p + pl * n + w + 2);
+      const float* pw = padd(p, w);
+      const float t0 = __ldg(p), t1 = __ldg(p + 1), t2 = __ldg(p + 2);
+      const float u0 = __ldg(pw), u1 = __ldg(pw + 1), u2 = __ldg(pw + 2);
       ra[pl] = a00 * t0 + a01 * t1 + a10 * u0 + a11 * u1;
       rb[pl] = b00 * t1 + b01 * t2 + b10 * u1 + b11 * u2;
+      p = padd(p, n);
     }
     um_finish(q[0].x, q[1].x, q[2].x, q[3].x, q[4].x, true, ra[0], ra[1], ra[2], ra[3], ra[4], w, h, x, y, fa.x, fa.y, ma);
     um_finish(q[0].y, q[1].y, q[2].y, q[3].y, q[4].y, true, rb[0], rb[1], rb[2], rb[3], rb[4], w, h, x + 1, y, fb.x, fb.y, mb);
@@ -954,10 +973,12 @@ __device__ __forceinline__ void update_matrices_px(const float* __restrict__ R0,
 __device__ __forceinline__ void update_matrices_vpair(const float* __restrict__ R0, const float* __restrict__ R1, int n,
                                                       int w, int h, int x, int y, float2 fa, float2 fb, float ma[5],
                                                       float mb[5]) {
-  const int o = y * w + x;
   float qa[5], qb[5];
+  {
+    const float* q = padd(R0, y * w + x);
 #pragma unroll
-  for (int c = 0; c < 5; ++c) { qa[c] = __ldg(R0 + c * n + o); qb[c] = __ldg(R0 + c * n + o + w); }
+    for (int c = 0; c < 5; ++c) { qa[c] = __ldg(q); qb[c] = __ldg(padd(q, w)); q = padd(q, n); }
+  }
   float fxa = (float)x + fa.x, fya = (float)y + fa.y;
   float fxb = (float)x + fb.x, fyb = (float)(y + 1) + fb.y;
   const int x1a = __float2int_rd(fxa), y1a = __float2int_rd(fya);
@@ -968,15 +989,18 @@ __device__ __forceinline__ void update_matrices_vpair(const float* __restrict__ 
     fxa -= (float)x1a; fya -= (float)y1a; fxb -= (float)x1b; fyb -= (float)y1b;
     const float a00 = (1.f - fxa) * (1.f - fya), a01 = fxa * (1.f - fya), a10 = (1.f - fxa) * fya, a11 = fxa * fya;
     const float b00 = (1.f - fxb) * (1.f - fyb), b01 = fxb * (1.f - fyb), b10 = (1.f - fxb) * fyb, b11 = fxb * fyb;
-    const float* p = R1 + (y1a * w + x1a);
+    const float* p = padd(R1, y1a * w + x1a);
     float ra[5], rb[5];
 #pragma unroll
     for (int pl = 0; pl < 5; ++pl) {
-      const float t00 = __ldg(p + pl * n), t01 = __ldg(p + pl * n + 1);
-      const float t10 = __ldg(p + pl * n + w), t11 = __ldg(p + pl * n + w + 1);
-      const float t20 = __ldg(p + pl * n + 2 * w), t21 = __ldg(p + pl * n + 2 * w + 1);
+      const float* p1 = padd(p, w);
+      const float* p2 = padd(p1, w);
+      const float t00 = __ldg(p), t01 = __ldg(p + 1);
+      const float t10 = __ldg(p1), t11 = __ldg(p1 + 1);
+      const float t20 = __ldg(p2), t21 = __ldg(p2 + 1);
       ra[pl] = a00 * t00 + a01 * t01 + a10 * t10 + a11 * t11;
       rb[pl] = b00 * t10 + b01 * t11 + b10 * t20 + b11 * t21;
+      p = padd(p, n);
     }
     um_finish(qa[0], qa[1], qa[2], qa[3], qa[4], true, ra[0], ra[1], ra[2], ra[3], ra[4], w, h, x, y, fa.x, fa.y, ma);
     um_finish(qb[0], qb[1], qb[2], qb[3], qb[4], true, rb[0], rb[1], rb[2], rb[3], rb[4], w, h, x, y + 1, fb.x, fb.y, mb);
@@ -1144,11 +1168,14 @@ updmat_init_kernel(const float* __restrict__ R, const float* __restrict__ flow_c
   float* Mo = M + (size_t)pair * 5 * n + o;
   if (two && (w & 1) == 0) {
     float2 q[5];
+    {
+      const float* qp = padd(R0, o);
 #pragma unroll
-    for (int c = 0; c < 5; ++c) q[c] = __ldg(reinterpret_cast<const float2*>(R0 + c * n + o));
+      for (int c = 0; c < 5; ++c) { q[c] = __ldg(reinterpret_cast<const float2*>(qp)); qp = padd(qp, n); }
+    }
     update_matrices_pair(q, R1, n, w, h, x, y, da, db, ma, mb);
 #pragma unroll
-    for (int c = 0; c < 5; ++c) *reinterpret_cast<float2*>(Mo + c * n) = make_float2(ma[c], mb[c]);
+    for (int c = 0; c < 5; ++c) { *reinterpret_cast<float2*>(Mo) = make_float2(ma[c], mb[c]); Mo = padd(Mo, n); }
   } else {
     update_matrices_px(R0, R1, n, w, h, x, y, da.x, da.y, ma);
 #pragma unroll
@@ -1372,7 +1399,7 @@ __device__ __forceinline__ void iter15_global_phase(const float2* fl, unsigned* 
       if (y + 1 < h) {
         update_matrices_vpair(R0, R1, ni, w, h, x, y, fa, fb, ma, mb);
 #pragma unroll
-        for (int c = 0; c < 5; ++c) { Mo[c * ni] = ma[c]; Mo[c * ni + w] = mb[c]; }
+        for (int c = 0; c < 5; ++c) { *Mo = ma[c]; *padd(Mo, w) = mb[c]; Mo = padd(Mo, ni); }
       } else {
         update_matrices_px(R0, R1, ni, w, h, x, y, fa.x, fa.y, ma);
 #pragma unroll
@@ -1730,10 +1757,12 @@ static_assert(2 * kTmStageBytes + 2 * kFiVtWords * sizeof(float) <= kWinSmemBars
 __device__ __forceinline__ void um_vpair_win(const float* __restrict__ R0, const float* __restrict__ R1, const float* __restrict__ win,
                                              int wx0, int wy0, bool fits, int n, int w, int h, int x, int y, float2 fa, float2 fb,
                                              float ma[5], float mb[5]) {
-  const int o = y * w + x;
   float qa[5], qb[5];
+  {
+    const float* q = padd(R0, y * w + x);
 #pragma unroll
-  for (int c = 0; c < 5; ++c) { qa[c] = __ldg(R0 + c * n + o); qb[c] = __ldg(R0 + c * n + o + w); }
+    for (int c = 0; c < 5; ++c) { qa[c] = __ldg(q); qb[c] = __ldg(padd(q, w)); q = padd(q, n); }
+  }
   float fxa = (float)x + fa.x, fya = (float)y + fa.y;
   float fxb = (float)x + fb.x, fyb = (float)(y + 1) + fb.y;
   const int x1a = __float2int_rd(fxa), y1a = __float2int_rd(fya);
@@ -1756,14 +1785,17 @@ __device__ __forceinline__ void um_vpair_win(const float* __restrict__ R0, const
         rb[pl] = b00 * t10 + b01 * t11 + b10 * t20 + b11 * t21;
       }
     } else {
-      const float* p = R1 + (y1a * w + x1a);
+      const float* p = padd(R1, y1a * w + x1a);
 #pragma unroll
       for (int pl = 0; pl < 5; ++pl) {
-        const float t00 = __ldg(p + pl * n), t01 = __ldg(p + pl * n + 1);
-        const float t10 = __ldg(p + pl * n + w), t11 = __ldg(p + pl * n + w + 1);
-        const float t20 = __ldg(p + pl * n + 2 * w), t21 = __ldg(p + pl * n + 2 * w + 1);
+        const float* p1 = padd(p, w);
+        const float* p2 = padd(p1, w);
+        const float t00 = __ldg(p), t01 = __ldg(p + 1);
+        const float t10 = __ldg(p1), t11 = __ldg(p1 + 1);
+        const float t20 = __ldg(p2), t21 = __ldg(p2 + 1);
         ra[pl] = a00 * t00 + a01 * t01 + a10 * t10 + a11 * t11;
         rb[pl] = b00 * t10 + b01 * t11 + b10 * t20 + b11 * t21;
+        p = padd(p, n);
       }
     }
     um_finish(qa[0], qa[1], qa[2], qa[3], qa[4], true, ra[0], ra[1], ra[2], ra[3], ra[4], w, h, x, y, fa.x, fa.y, ma);
@@ -1927,7 +1959,7 @@ iter15_win_kernel(const STB_GRID_CONSTANT TmaMap3D map_in, float* __restrict__ M
     if (y + 1 < h) {
       um_vpair_win(R0, R1, win, wx0, wy0, fits, ni, w, h, x, y, fa, fb, ma, mb);
 #pragma unroll
-      for (int c = 0; c < 5; ++c) { Mo[c * ni] = ma[c]; Mo[c * ni + w] = mb[c]; }
+      for (int c = 0; c < 5; ++c) { *Mo = ma[c]; *padd(Mo, w) = mb[c]; Mo = padd(Mo, ni); }
     } else {
       update_matrices_px(R0, R1, ni, w, h, x, y, fa.x, fa.y, ma);
 #pragma unroll
