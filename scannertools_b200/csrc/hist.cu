@@ -2,9 +2,9 @@
 //
 // All four are HBM-bound byte/word streaming kernels: each input byte is read exactly once
 // with 16-byte coalesced loads; counting happens in shared memory that is privatised per
-// warp AND per lane (bank == lane), so shared-memory atomics never conflict regardless of
-// image content (constant frames are the worst case for a shared table); one global merge
-// per block.
+// lane (bank == lane), so shared-memory reductions never conflict regardless of image content
+// (constant frames are the worst case for a shared table); the RGB histogram counts byte PAIRS
+// into a joint table (half the reductions); one global merge per block.
 //
 // Reference call sites replaced: see include/stb.h.
 #include <cstdlib>
@@ -29,52 +29,72 @@ struct StrideAddrU8 {
 // offset a belongs to channel a % 3 and falls in bin (byte >> 4).
 // Block = 384 threads (a multiple of 3 and of 32), so with a grid-stride of gridDim.x*384
 // sixteen-byte vectors every thread sees a constant channel phase: byte b of each of its
-// vectors is channel (phase + b) % 3 -- the three table bases are fixed registers.
+// vectors is channel (phase + b) % 3 -- the table bases are fixed registers.
+//
+// JOINT counting: a shared-memory reduction costs ~2 cycles of the SM's atomic unit per warp
+// instruction whatever it adds and however many lanes are active (tools/probe/atoms_probe.cu), so one
+// RED per input byte caps the kernel at ~17 B/clk/SM = 0.75 of HBM -- where round 1 / early round 2
+// sat.  Two vectors of one thread have the same channel phase, so byte k of vector A and byte k of
+// vector B are the same channel: the pair is counted with ONE reduction into a 256-entry joint table
+// indexed by (bin_A | bin_B << 4), and the block's epilogue folds the joint table into the two
+// marginals.  Half the reductions for any content, and fewer instructions per byte (the joint indices
+// of four byte pairs come from one shift + one LOP3 on the two words).
+// Tables are private per LANE (bank == lane, never a conflict); one table per block -- updates of
+// different warps are different instructions and serialise in the atomic unit anyway.
+//   joint  [3 channels][256][32 lanes] u32 = 96 KB, single [3][16][32] u32 = 6 KB (odd vector, ragged ends)
 // -------------------------------------------------------------------------------------------
 constexpr int kHistThreads = 384;
-constexpr int kHistWarps = kHistThreads / 32;
-// table layout: [warp][channel][bin][lane] u32 -> byte offset ((warp*3 + ch)*16 + bin)*128 + lane*4.
-// The origin is aligned to 2048 bytes inside the dynamic allocation, so for a fixed (warp, ch,
-// lane) the bin only occupies address bits 7..10 and "base | (bin << 7)" needs no add.
-constexpr int kHistTableBytes = kHistWarps * STB_HIST_INTS * 32 * 4;   // 72 KB
-constexpr int kHistSmemBytes = kHistTableBytes + 2048;                 // + alignment slack
+constexpr int kHistBlocksPerSM = 2;
+constexpr int kHistJointBytes = 3 * 256 * 32 * 4;                       // 98304
+constexpr int kHistSingleBytes = STB_HIST_INTS * 32 * 4;                // 6144
+constexpr int kHistSmemBytes = kHistJointBytes + kHistSingleBytes;      // 104448: two blocks per SM
 
 #ifdef STB_CPU_EMU
-typedef unsigned char* hist_addr_t;   // emulator: a plain pointer into the aligned table
-__device__ __forceinline__ hist_addr_t hist_origin(unsigned char* dyn) {
-  return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dyn) + 2047) & ~(uintptr_t)2047);
-}
-__device__ __forceinline__ void hist_inc(hist_addr_t base, unsigned off) {
-  atomicAdd(reinterpret_cast<unsigned*>(reinterpret_cast<uintptr_t>(base) | off), 1u);
-}
-__device__ __forceinline__ unsigned* hist_ptr(hist_addr_t origin, unsigned byte_off) {
-  return reinterpret_cast<unsigned*>(origin + byte_off);
-}
+typedef unsigned char* hist_addr_t;   // emulator: a plain pointer into the table
+__device__ __forceinline__ hist_addr_t hist_origin(unsigned char* dyn) { return dyn; }
+__device__ __forceinline__ void hist_inc(hist_addr_t a) { atomicAdd(reinterpret_cast<unsigned*>(a), 1u); }
+__device__ __forceinline__ unsigned hist_byte(unsigned w, int k) { return (w >> (8 * k)) & 255u; }
 #else
 typedef unsigned hist_addr_t;         // 32-bit address in the shared window
-__device__ __forceinline__ hist_addr_t hist_origin(unsigned char* dyn) {
-  return ((unsigned)__cvta_generic_to_shared(dyn) + 2047u) & ~2047u;
+__device__ __forceinline__ hist_addr_t hist_origin(unsigned char* dyn) { return (unsigned)__cvta_generic_to_shared(dyn); }
+__device__ __forceinline__ void hist_inc(hist_addr_t a) {
+  asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory");   // fire-and-forget shared-memory reduction
 }
-__device__ __forceinline__ void hist_inc(hist_addr_t base, unsigned off) {
-  // fire-and-forget shared-memory reduction; (base | off) is one LOP3 fused with the mask
-  asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(base | off) : "memory");
-}
-__device__ __forceinline__ unsigned* hist_ptr(hist_addr_t origin, unsigned byte_off) {
-  return reinterpret_cast<unsigned*>(__cvta_shared_to_generic((size_t)(origin + byte_off)));
-}
+__device__ __forceinline__ unsigned hist_byte(unsigned w, int k) { return __byte_perm(w, 0u, 0x4440u + (unsigned)k); }
 #endif
 
+// four byte pairs (byte k of wa with byte k of wb); their channels use bases (b0, b1, b2, b0): the caller
+// rotates them per word.  m holds the four joint indices, one per byte: bin_A in the low nibble, bin_B in the high.
+__device__ __forceinline__ void hist_count_pair_word(unsigned wa, unsigned wb, hist_addr_t b0, hist_addr_t b1, hist_addr_t b2) {
+#ifdef STB_CPU_EMU
+  const unsigned m = ((wa >> 4) & 0x0f0f0f0fu) | (wb & 0xf0f0f0f0u);
+#else
+  unsigned m;   // bitwise select in one LOP3: mask ? (wa >> 4) : wb
+  asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(m) : "r"(0x0f0f0f0fu), "r"(wa >> 4), "r"(wb));
+#endif
+  hist_inc(b0 + (hist_byte(m, 0) << 7));
+  hist_inc(b1 + (hist_byte(m, 1) << 7));
+  hist_inc(b2 + (hist_byte(m, 2) << 7));
+  hist_inc(b0 + (hist_byte(m, 3) << 7));
+}
+
+__device__ __forceinline__ void hist_count_pair_vec(const uint4& a, const uint4& b, hist_addr_t c0, hist_addr_t c1, hist_addr_t c2) {
+  // word j starts at byte 4j: channel of its first byte is (phase + 4j) % 3 = (phase + j) % 3
+  hist_count_pair_word(a.x, b.x, c0, c1, c2);
+  hist_count_pair_word(a.y, b.y, c1, c2, c0);
+  hist_count_pair_word(a.z, b.z, c2, c0, c1);
+  hist_count_pair_word(a.w, b.w, c0, c1, c2);
+}
+
 __device__ __forceinline__ void hist_count_word(unsigned wd, hist_addr_t b0, hist_addr_t b1, hist_addr_t b2) {
-  // bytes k = 0..3 of this word use bases (b0,b1,b2,b0): the caller rotates them per word.
-  // bin << 7 == ((byte >> 4) & 15) << 7, taken straight out of the word with one shift + mask.
-  hist_inc(b0, (wd << 3) & 0x780u);
-  hist_inc(b1, (wd >> 5) & 0x780u);
-  hist_inc(b2, (wd >> 13) & 0x780u);
-  hist_inc(b0, (wd >> 21) & 0x780u);
+  // single bytes: bin << 7 == ((byte >> 4) & 15) << 7, taken straight out of the word with one shift + mask
+  hist_inc(b0 + ((wd << 3) & 0x780u));
+  hist_inc(b1 + ((wd >> 5) & 0x780u));
+  hist_inc(b2 + ((wd >> 13) & 0x780u));
+  hist_inc(b0 + ((wd >> 21) & 0x780u));
 }
 
 __device__ __forceinline__ void hist_count_vec(const uint4& q, hist_addr_t c0, hist_addr_t c1, hist_addr_t c2) {
-  // word j starts at byte 4j: channel of its first byte is (phase + 4j) % 3 = (phase + j) % 3
   hist_count_word(q.x, c0, c1, c2);
   hist_count_word(q.y, c1, c2, c0);
   hist_count_word(q.z, c2, c0, c1);
@@ -82,7 +102,7 @@ __device__ __forceinline__ void hist_count_vec(const uint4& q, hist_addr_t c0, h
 }
 
 template <class Addr>
-__global__ void __launch_bounds__(kHistThreads, 3)
+__global__ void __launch_bounds__(kHistThreads, kHistBlocksPerSM)
 hist_rgb16_kernel(Addr addr, unsigned long long nbytes, int32_t* __restrict__ out, unsigned base_blocks, unsigned rem) {
   // 1-D grid over (frame, part): the first `rem` frames get base_blocks + 1 blocks, the others
   // base_blocks, so a batch fills the resident wave exactly whatever the frame count
@@ -90,10 +110,10 @@ hist_rgb16_kernel(Addr addr, unsigned long long nbytes, int32_t* __restrict__ ou
   flat_grid_decode(blockIdx.x, base_blocks, rem, frame, part, nparts);
   STB_DYN_SMEM(unsigned char, dyn);
   const hist_addr_t origin = hist_origin(dyn);
-  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const unsigned tid = threadIdx.x, lane = tid & 31u;
   {
-    uint4* z = reinterpret_cast<uint4*>(hist_ptr(origin, 0));
-    for (unsigned i = tid; i < kHistTableBytes / 16; i += kHistThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    uint4* z = reinterpret_cast<uint4*>(dyn);
+    for (unsigned i = tid; i < kHistSmemBytes / 16; i += kHistThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();
 
@@ -106,32 +126,34 @@ hist_rgb16_kernel(Addr addr, unsigned long long nbytes, int32_t* __restrict__ ou
   const unsigned gt = part * kHistThreads + tid;
   const unsigned long long T = (unsigned long long)nparts * kHistThreads;
   const unsigned ph = (unsigned)((head + gt) % 3u);
-  const hist_addr_t wbase = origin + warp * (3u * 2048u) + lane * 4u;
-  const hist_addr_t c0 = wbase + ((ph + 0u) % 3u) * 2048u;
-  const hist_addr_t c1 = wbase + ((ph + 1u) % 3u) * 2048u;
-  const hist_addr_t c2 = wbase + ((ph + 2u) % 3u) * 2048u;
+  const hist_addr_t jbase = origin + lane * 4u, sbase = origin + kHistJointBytes + lane * 4u;
+  const hist_addr_t j0 = jbase + ((ph + 0u) % 3u) * 32768u, j1 = jbase + ((ph + 1u) % 3u) * 32768u,
+                    j2 = jbase + ((ph + 2u) % 3u) * 32768u;
+  const hist_addr_t s0 = sbase + ((ph + 0u) % 3u) * 2048u, s1 = sbase + ((ph + 1u) % 3u) * 2048u,
+                    s2 = sbase + ((ph + 2u) % 3u) * 2048u;
 
-  // software pipeline: the next four vectors are in flight while the current four are counted
+  // software pipeline: the next four vectors are in flight while the current four (two pairs) are counted
   unsigned long long i = gt;
   if (i + 3 * T < nvec) {
     uint4 q0 = __ldg(v + i), q1 = __ldg(v + i + T), q2 = __ldg(v + i + 2 * T), q3 = __ldg(v + i + 3 * T);
     i += 4 * T;
+#pragma unroll 2
     for (; i + 3 * T < nvec; i += 4 * T) {
       const uint4 n0 = __ldg(v + i), n1 = __ldg(v + i + T), n2 = __ldg(v + i + 2 * T), n3 = __ldg(v + i + 3 * T);
-      hist_count_vec(q0, c0, c1, c2);
-      hist_count_vec(q1, c0, c1, c2);
-      hist_count_vec(q2, c0, c1, c2);
-      hist_count_vec(q3, c0, c1, c2);
+      hist_count_pair_vec(q0, q1, j0, j1, j2);
+      hist_count_pair_vec(q2, q3, j0, j1, j2);
       q0 = n0; q1 = n1; q2 = n2; q3 = n3;
     }
-    hist_count_vec(q0, c0, c1, c2);
-    hist_count_vec(q1, c0, c1, c2);
-    hist_count_vec(q2, c0, c1, c2);
-    hist_count_vec(q3, c0, c1, c2);
+    hist_count_pair_vec(q0, q1, j0, j1, j2);
+    hist_count_pair_vec(q2, q3, j0, j1, j2);
   }
-  for (; i < nvec; i += T) {
+  for (; i + T < nvec; i += 2 * T) {
+    const uint4 qa = __ldg(v + i), qb = __ldg(v + i + T);
+    hist_count_pair_vec(qa, qb, j0, j1, j2);
+  }
+  if (i < nvec) {
     const uint4 q = __ldg(v + i);
-    hist_count_vec(q, c0, c1, c2);
+    hist_count_vec(q, s0, s1, s2);
   }
   // ragged ends (unaligned base pointer / byte count not a multiple of 16): at most 30 bytes
   if (part == 0) {
@@ -139,18 +161,27 @@ hist_rgb16_kernel(Addr addr, unsigned long long nbytes, int32_t* __restrict__ ou
     const unsigned long long ntail = nbytes - tail0;
     if (tid < head + ntail) {
       const unsigned long long a = tid < head ? tid : tail0 + (tid - head);
-      hist_inc(wbase + (unsigned)(a % 3u) * 2048u, ((unsigned)(f[a] >> 4)) << 7);
+      hist_inc(sbase + (unsigned)(a % 3u) * 2048u + (((unsigned)(f[a] >> 4)) << 7));
     }
   }
   __syncthreads();
 
-  // block reduce: 8 threads per bin (bin = ch*16 + b), each sums 4 lanes x 12 warps
+  // block reduce: 8 threads per output bin (ch, b), each over 4 lanes: the single table's row plus the
+  // joint table's rows (b | j << 4) -- first byte of a pair in bin b -- and (j | b << 4) -- second byte
   const unsigned bin = tid >> 3, rpart = tid & 7u;
-  unsigned s = 0;
-#pragma unroll
-  for (int w = 0; w < kHistWarps; ++w) {
-    const uint4 q = *reinterpret_cast<const uint4*>(hist_ptr(origin, ((w * STB_HIST_INTS + bin) * 32 + rpart * 4) * 4));
-    s += q.x + q.y + q.z + q.w;
+  const unsigned ch = bin >> 4, b = bin & 15u;
+  const unsigned* jt = reinterpret_cast<const unsigned*>(dyn) + ch * (256 * 32) + rpart * 4;
+  const unsigned* st = reinterpret_cast<const unsigned*>(dyn + kHistJointBytes) + bin * 32 + rpart * 4;
+  unsigned s;
+  {
+    const uint4 q = *reinterpret_cast<const uint4*>(st);
+    s = q.x + q.y + q.z + q.w;
+  }
+#pragma unroll 4
+  for (unsigned j = 0; j < 16; ++j) {
+    const uint4 qa = *reinterpret_cast<const uint4*>(jt + (b | (j << 4)) * 32);
+    const uint4 qb = *reinterpret_cast<const uint4*>(jt + (j | (b << 4)) * 32);
+    s += qa.x + qa.y + qa.z + qa.w + qb.x + qb.y + qb.z + qb.w;
   }
   s += __shfl_xor_sync(0xffffffffu, s, 1);
   s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -346,10 +377,10 @@ static int launch_hist(Addr addr, int n, unsigned long long nbytes, int32_t* d_o
     attr_done[dev] = true;
   }
   const unsigned long long nvec = nbytes >> 4;
-  // one resident wave (3 blocks/SM) spread over the frames of this launch; never more blocks
+  // one resident wave (kHistBlocksPerSM blocks/SM) spread over the frames of this launch; never more blocks
   // than there are 4-vector iterations of work
-  const int wave = num_sms() * 3;
-  // Total blocks: one resident wave (3 blocks/SM) split over the frames as evenly as possible
+  const int wave = num_sms() * kHistBlocksPerSM;
+  // Total blocks: one resident wave split over the frames as evenly as possible
   // (some frames get one block more); spilling a handful of blocks into a second wave costs ~25 %,
   // leaving slots empty costs proportionally (n = 32 on 444 slots: 416 blocks 66.8 %, 444 blocks ~71 %).
   // Never more blocks per frame than there are 4-vector iterations of work; with more frames than
