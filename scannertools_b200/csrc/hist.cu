@@ -45,6 +45,10 @@ struct StrideAddrU8 {
 // -------------------------------------------------------------------------------------------
 constexpr int kHistThreads = 384;
 constexpr int kHistBlocksPerSM = 2;
+#ifndef STB_HIST_VECS
+#define STB_HIST_VECS 4
+#endif
+constexpr int kHistVecs = STB_HIST_VECS;                                // 16-byte vectors in flight per thread (even)
 constexpr int kHistJointBytes = 3 * 256 * 32 * 4;                       // 98304
 constexpr int kHistSingleBytes = STB_HIST_INTS * 32 * 4;                // 6144
 constexpr int kHistSmemBytes = kHistJointBytes + kHistSingleBytes;      // 104448: two blocks per SM
@@ -132,20 +136,25 @@ hist_rgb16_kernel(Addr addr, unsigned long long nbytes, int32_t* __restrict__ ou
   const hist_addr_t s0 = sbase + ((ph + 0u) % 3u) * 2048u, s1 = sbase + ((ph + 1u) % 3u) * 2048u,
                     s2 = sbase + ((ph + 2u) % 3u) * 2048u;
 
-  // software pipeline: the next four vectors are in flight while the current four (two pairs) are counted
+  // software pipeline: the next kHistVecs vectors are in flight while the current ones (kHistVecs / 2 pairs) are counted
   unsigned long long i = gt;
-  if (i + 3 * T < nvec) {
-    uint4 q0 = __ldg(v + i), q1 = __ldg(v + i + T), q2 = __ldg(v + i + 2 * T), q3 = __ldg(v + i + 3 * T);
-    i += 4 * T;
+  if (i + (kHistVecs - 1) * T < nvec) {
+    uint4 q[kHistVecs];
+#pragma unroll
+    for (int k = 0; k < kHistVecs; ++k) q[k] = __ldg(v + i + k * T);
+    i += kHistVecs * T;
 #pragma unroll 2
-    for (; i + 3 * T < nvec; i += 4 * T) {
-      const uint4 n0 = __ldg(v + i), n1 = __ldg(v + i + T), n2 = __ldg(v + i + 2 * T), n3 = __ldg(v + i + 3 * T);
-      hist_count_pair_vec(q0, q1, j0, j1, j2);
-      hist_count_pair_vec(q2, q3, j0, j1, j2);
-      q0 = n0; q1 = n1; q2 = n2; q3 = n3;
+    for (; i + (kHistVecs - 1) * T < nvec; i += kHistVecs * T) {
+      uint4 nx[kHistVecs];
+#pragma unroll
+      for (int k = 0; k < kHistVecs; ++k) nx[k] = __ldg(v + i + k * T);
+#pragma unroll
+      for (int k = 0; k < kHistVecs; k += 2) hist_count_pair_vec(q[k], q[k + 1], j0, j1, j2);
+#pragma unroll
+      for (int k = 0; k < kHistVecs; ++k) q[k] = nx[k];
     }
-    hist_count_pair_vec(q0, q1, j0, j1, j2);
-    hist_count_pair_vec(q2, q3, j0, j1, j2);
+#pragma unroll
+    for (int k = 0; k < kHistVecs; k += 2) hist_count_pair_vec(q[k], q[k + 1], j0, j1, j2);
   }
   for (; i + T < nvec; i += 2 * T) {
     const uint4 qa = __ldg(v + i), qb = __ldg(v + i + T);
