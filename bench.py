@@ -481,7 +481,7 @@ def run_ours(args):
             'config': workload_config(args),
             'host': {'numa_node_rank0': numa_node, 'cores': host_cores()},
             'hbm_roofline_frac_whole_op': (FLOW1080_BYTES + FLOWHIST1080_BYTES) * value / world / (peak * 1e9),
-            'roofline': {'bound': 'hbm', 'kernel': 'iter15_tma_kernel<true,false> (level-0 fused box-sum / 2x2 solve / update-matrices iteration, TMA-staged M tiles)',
+            'roofline': {'bound': 'hbm', 'kernel': 'iter15_win_kernel (level-0 fused box-sum / 2x2 solve / update-matrices iteration: TMA-staged M tiles, flow-compensated R1 window in shared memory)',
                          'achieved': achieved, 'peak': peak, 'peak_kind': peak_kind, 'unit': 'GB/s',
                          'frac': (achieved / peak) if achieved else None,
                          'bytes_per_launch': iter_bytes, 'pairs_per_launch': pairs_per_launch, 'avg_launch_us': avg_iter_s * 1e6,

@@ -154,9 +154,12 @@ STB_API int stb_resize_target(int frame_w, int frame_h, int width, int height, i
 STB_API int stb_resize_bilinear_u8(const uint8_t* const* d_src, int n, int src_w, int src_h, int channels,
                                    uint8_t* const* d_dst, int dst_w, int dst_h, stb_stream_t stream);
 /* The same with ResizeArgs.interpolation (resize_kernel.cpp:9-20,31-35): stb_resize_interp_code maps
- * "INTER_LINEAR" (also "" / NULL, the reference's default), "INTER_NEAREST", "INTER_AREA" to codes
- * 0, 1, 2 and anything else to -1 (stb_resize_u8 then returns STB_ERR_UNSUPPORTED).  Bit-exact with
- * cv::resize on 8-bit frames for all three. */
+ * "INTER_LINEAR" (also "" / NULL, the reference's default), "INTER_NEAREST", "INTER_AREA", "INTER_CUBIC",
+ * "INTER_LANCZOS4" to codes 0..4 and anything else to -1 (stb_resize_u8 then returns
+ * STB_ERR_UNSUPPORTED).  Bit-exact with cv::resize on 8-bit frames for all five (INTER_CUBIC: with
+ * OpenCV's own code path; OpenCV builds that hand 8-bit cubic to IPP differ from it by one grey level on
+ * ~5 % of pixels).  INTER_CUBIC / INTER_LANCZOS4 build their tap tables on the host and upload them in
+ * stream order (cudaMallocAsync / cudaFreeAsync): the call stays asynchronous but is not graph-capturable. */
 STB_API int stb_resize_interp_code(const char* name);
 STB_API int stb_resize_u8(const uint8_t* const* d_src, int n, int src_w, int src_h, int channels,
                           uint8_t* const* d_dst, int dst_w, int dst_h, int interp, stb_stream_t stream);

@@ -601,7 +601,108 @@ ORC_API void orc_resize_linear_u8(const uint8_t* src, int sw, int sh, int cn, ui
  *   AREA with an up-scaled axis: INTER_LINEAR arithmetic with the "area" coefficient
  *         fx = (dx+1) - (sx+1)*inv_scale, sx = floor(dx*scale).
  * Verified bit-exact against cv2 4.13 (tests/test_oracle.py). */
-enum { ORC_INTER_LINEAR = 0, ORC_INTER_NEAREST = 1, ORC_INTER_AREA = 2 };
+enum { ORC_INTER_LINEAR = 0, ORC_INTER_NEAREST = 1, ORC_INTER_AREA = 2, ORC_INTER_CUBIC = 3, ORC_INTER_LANCZOS4 = 4 };
+
+/* ---- INTER_CUBIC / INTER_LANCZOS4 on 8-bit frames (resize_kernel.cpp:13,15), OpenCV's own generic
+ * path (imgproc/src/resize.cpp resizeGeneric_, HResizeCubic / HResizeLanczos4 <uchar,int,short>):
+ *   per destination index: f = (float)((d + 0.5) * scale - 0.5), s = floor(f), f -= s, K float taps
+ *   (interpolateCubic, A = -0.75 / interpolateLanczos4), shorts saturate_cast<short>(tap * 2048);
+ *   tap k reads source index clamp(s - (K/2 - 1) + k); horizontal pass in int; vertical pass:
+ *   cubic -- VResizeCubicVec_32s8u for the first floor(W*cn/8)*8 elements of a row (128-bit universal
+ *   intrinsics: float, beta * 2^-22, S3*b3 + S2*b2 + S1*b1 + S0*b0 accumulated in that order with
+ *   separately rounded mul / add, round half even), (sum + 2^21) >> 22 in int for the scalar tail;
+ *   Lanczos4 -- int only.  Verified bit-exact against cv2 4.13 with cv2.ipp.setUseIPP(False): this
+ *   wheel otherwise dispatches 8-bit INTER_CUBIC to IPP, whose output differs from OpenCV's own code
+ *   by one grey level on ~5 % of pixels (tests/test_oracle.py bounds that too). */
+static uint8_t sat_u8_f(float v) { long r = lrintf(v); return (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r)); }
+
+static void orc_cubic_coeffs(float x, float* c) {
+  const float A = -0.75f;
+  c[0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
+  c[1] = ((A + 2) * x - (A + 3)) * x * x + 1;
+  c[2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
+  c[3] = 1.f - c[0] - c[1] - c[2];
+}
+
+static void orc_lanczos4_coeffs(float x, float* c) {
+  static const double s45 = 0.70710678118654752440;
+  static const double cs[][2] = {{1, 0}, {-s45, -s45}, {0, 1}, {s45, -s45}, {-1, 0}, {s45, s45}, {0, -1}, {-s45, s45}};
+  if (x < 1.1920928955078125e-07f) { for (int i = 0; i < 8; ++i) c[i] = 0.f; c[3] = 1.f; return; }
+  float sum = 0.f;
+  double y0 = -(x + 3) * 3.1415926535897932384626433832795 * 0.25, s0 = sin(y0), c0 = cos(y0);
+  for (int i = 0; i < 8; ++i) {
+    double y = -(x + 3 - i) * 3.1415926535897932384626433832795 * 0.25;
+    c[i] = (float)((cs[i][0] * s0 + cs[i][1] * c0) / (y * y));
+    sum += c[i];
+  }
+  sum = 1.f / sum;
+  for (int i = 0; i < 8; ++i) c[i] *= sum;
+}
+
+static void orc_taps(int dn, int sn, int K, int cubic, int* ofs, short* al) {
+  double scale = 1. / ((double)dn / sn);
+  for (int d = 0; d < dn; ++d) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s0 = (int)floor(f);
+    f -= s0;
+    float c[8];
+    if (cubic) orc_cubic_coeffs(f, c); else orc_lanczos4_coeffs(f, c);
+    ofs[d] = s0 - (K / 2 - 1);
+    for (int k = 0; k < K; ++k) {
+      long r = lrintf(c[k] * 2048.f);
+      al[d * K + k] = (short)(r < -32768 ? -32768 : (r > 32767 ? 32767 : r));
+    }
+  }
+}
+
+static void resize_taps_u8(const uint8_t* src, int sw, int sh, int cn, uint8_t* dst, int dw, int dh, int cubic) {
+  const int K = cubic ? 4 : 8, W = dw * cn;
+  int* xofs = (int*)malloc(sizeof(int) * (size_t)dw); short* xa = (short*)malloc(sizeof(short) * (size_t)dw * K);
+  int* yofs = (int*)malloc(sizeof(int) * (size_t)dh); short* ya = (short*)malloc(sizeof(short) * (size_t)dh * K);
+  orc_taps(dw, sw, K, cubic, xofs, xa);
+  orc_taps(dh, sh, K, cubic, yofs, ya);
+  int* rows = (int*)malloc(sizeof(int) * (size_t)W * K);   /* the K horizontally resampled source rows of one output row */
+  const int nvec = cubic ? (W / 8) * 8 : 0;
+  for (int dy = 0; dy < dh; ++dy) {
+    for (int j = 0; j < K; ++j) {
+      int sy = yofs[dy] + j; sy = sy < 0 ? 0 : (sy > sh - 1 ? sh - 1 : sy);
+      const uint8_t* S = src + (size_t)sy * sw * cn;
+      for (int dx = 0; dx < dw; ++dx)
+        for (int c = 0; c < cn; ++c) {
+          int h = 0;
+          for (int k = 0; k < K; ++k) {
+            int sx = xofs[dx] + k; sx = sx < 0 ? 0 : (sx > sw - 1 ? sw - 1 : sx);
+            h += S[sx * cn + c] * xa[dx * K + k];
+          }
+          rows[(size_t)j * W + dx * cn + c] = h;
+        }
+    }
+    const short* b = ya + (size_t)dy * K;
+    uint8_t* D = dst + (size_t)dy * W;
+    int x = 0;
+    if (cubic) {
+      const float sc = 1.f / (2048.f * 2048.f);
+      const float b0 = b[0] * sc, b1 = b[1] * sc, b2 = b[2] * sc, b3 = b[3] * sc;
+      for (; x < nvec; ++x) {
+        volatile float t3 = (float)rows[3 * (size_t)W + x] * b3;
+        volatile float t2 = (float)rows[2 * (size_t)W + x] * b2;
+        volatile float t1 = (float)rows[1 * (size_t)W + x] * b1;
+        volatile float t0 = (float)rows[x] * b0;
+        volatile float acc = t2 + t3;
+        acc = t1 + acc;
+        acc = t0 + acc;
+        D[x] = sat_u8_f(acc);
+      }
+    }
+    for (; x < W; ++x) {
+      int t = 0;
+      for (int j = 0; j < K; ++j) t += rows[(size_t)j * W + x] * b[j];
+      int v = (t + (1 << 21)) >> 22;
+      D[x] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+  }
+  free(rows); free(xofs); free(xa); free(yofs); free(ya);
+}
 
 typedef struct { int di, si; float alpha; } area_tab_t;
 
@@ -623,7 +724,6 @@ static int area_tab(int ssize, int dsize, double scale, area_tab_t* tab) {
   return k;
 }
 
-static uint8_t sat_u8_f(float v) { long r = lrintf(v); return (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r)); }
 
 static void resize_linear_area_mode(const uint8_t* src, int sw, int sh, int cn, uint8_t* dst, int dw, int dh) {
   double inv_x = (double)dw / sw, inv_y = (double)dh / sh, scale_x = 1. / inv_x, scale_y = 1. / inv_y;
@@ -665,6 +765,10 @@ ORC_API int orc_resize_u8(const uint8_t* src, int sw, int sh, int cn, uint8_t* d
         memcpy(dst + ((size_t)y * dw + x) * cn, src + ((size_t)sy * sw + sx) * cn, (size_t)cn);
       }
     }
+    return 0;
+  }
+  if (interp == ORC_INTER_CUBIC || interp == ORC_INTER_LANCZOS4) {
+    resize_taps_u8(src, sw, sh, cn, dst, dw, dh, interp == ORC_INTER_CUBIC);
     return 0;
   }
   if (interp != ORC_INTER_AREA) return -1;

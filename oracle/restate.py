@@ -123,7 +123,7 @@ def optical_flow(frame0, frame1):
     return out
 
 
-RESIZE_INTERP = {'INTER_LINEAR': 0, 'INTER_NEAREST': 1, 'INTER_AREA': 2}
+RESIZE_INTERP = {'INTER_LINEAR': 0, 'INTER_NEAREST': 1, 'INTER_AREA': 2, 'INTER_CUBIC': 3, 'INTER_LANCZOS4': 4}
 
 
 def resize(frame, width, height, interpolation='INTER_LINEAR'):

@@ -12,8 +12,20 @@
 // The other interpolation names the reference maps (resize_kernel.cpp:9-20) that are implemented:
 // INTER_NEAREST and INTER_AREA (integer-factor block averages, the general weighted-cell tables with
 // OpenCV's float accumulation order, and the linear "area" coefficients when an axis is up-scaled),
-// all bit-exact with cv2 4.13.  INTER_CUBIC / INTER_LANCZOS4 return STB_ERR_UNSUPPORTED.
+// all bit-exact with cv2 4.13.
+//
+// INTER_CUBIC / INTER_LANCZOS4 (resize_kernel.cpp:13,15): OpenCV's generic separable fixed-point path
+// (resizeGeneric_ with HResizeCubic / HResizeLanczos4 in int and 11-bit short coefficients).  The tap
+// tables (first source index + 4 / 8 shorts per destination column and row) are built on the HOST with
+// the same float / double expressions OpenCV uses (interpolateCubic, A = -0.75; interpolateLanczos4 with
+// libm's sin / cos) and uploaded stream-ordered; resize_taps_u8_kernel applies them.  The vertical pass
+// reproduces OpenCV's two code paths: VResizeCubicVec_32s8u combines the four int rows in float
+// (beta * 2^-22, mul / add without contraction, round half even) for the first floor(W * cn / 8) * 8
+// elements of a row and the exact integer (sum + 2^21) >> 22 for the scalar tail; Lanczos4 has no vector
+// path for 8-bit frames.  Bit-exact with cv2's own implementation (cv2.ipp.setUseIPP(False)); builds of
+// OpenCV that dispatch 8-bit cubic to IPP differ from OpenCV's own code by one grey level on ~5 % of pixels.
 #include <cmath>
+#include <vector>
 
 #include "stb_rt.h"
 
@@ -24,7 +36,7 @@ struct PtrAddrPairU8 {
   PtrBatch<uint8_t> dst;
 };
 
-enum { kInterpLinear = 0, kInterpNearest = 1, kInterpArea = 2 };
+enum { kInterpLinear = 0, kInterpNearest = 1, kInterpArea = 2, kInterpCubic = 3, kInterpLanczos4 = 4 };
 
 __device__ __forceinline__ int cv_round_f(float v) { return __float2int_rn(v); }
 
@@ -188,6 +200,113 @@ resize_area_u8_kernel(PtrBatch<const uint8_t> srcs, PtrBatch<uint8_t> dsts, int 
   for (int c = 0; c < CN; ++c) dst[c] = (uint8_t)min(max(__float2int_rn(sum[c]), 0), 255);
 }
 
+// INTER_CUBIC (K = 4) / INTER_LANCZOS4 (K = 8): host-built tap tables.  xofs / yofs = index of the first
+// tap (may be outside the image: taps are clamped to the border, cv::resizeGeneric_'s xmin / xmax handling);
+// xa / ya = K short coefficients per destination column / row.  One thread per output pixel.
+template <int CN, int K>
+__global__ void __launch_bounds__(256)
+resize_taps_u8_kernel(PtrBatch<const uint8_t> srcs, PtrBatch<uint8_t> dsts, int sw, int sh, int dw, int dh,
+                      const int* __restrict__ xofs, const short* __restrict__ xa, const int* __restrict__ yofs,
+                      const short* __restrict__ ya, int vec_elems) {
+  const int dx = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int dy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (dx >= dw || dy >= dh) return;
+  const uint8_t* src = srcs.p[blockIdx.z];
+  uint8_t* dst = dsts.p[blockIdx.z] + ((size_t)dy * dw + dx) * CN;
+  const int sx0 = xofs[dx], sy0 = yofs[dy];
+  int a[K], b[K], cx[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    a[k] = xa[dx * K + k];
+    b[k] = ya[dy * K + k];
+    cx[k] = min(max(sx0 + k, 0), sw - 1) * CN;
+  }
+  int hsum[K][CN];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const uint8_t* r = src + (size_t)min(max(sy0 + j, 0), sh - 1) * sw * CN;
+#pragma unroll
+    for (int c = 0; c < CN; ++c) {
+      int h = 0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) h += r[cx[k] + c] * a[k];
+      hsum[j][c] = h;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CN; ++c) {
+    int v;
+    if (K == 4 && dx * CN + c < vec_elems) {
+      // VResizeCubicVec_32s8u: float, S3 * b3 first, then + S2 * b2, + S1 * b1, + S0 * b0 (mul and add rounded separately)
+      const float sc = 1.f / (2048.f * 2048.f);
+      float acc = __fmul_rn((float)hsum[3][c], __fmul_rn((float)b[3], sc));
+      acc = __fadd_rn(__fmul_rn((float)hsum[2][c], __fmul_rn((float)b[2], sc)), acc);
+      acc = __fadd_rn(__fmul_rn((float)hsum[1][c], __fmul_rn((float)b[1], sc)), acc);
+      acc = __fadd_rn(__fmul_rn((float)hsum[0][c], __fmul_rn((float)b[0], sc)), acc);
+      v = __float2int_rn(acc);
+    } else {
+      int t = 0;
+#pragma unroll
+      for (int j = 0; j < K; ++j) t += hsum[j][c] * b[j];
+      v = (t + (1 << 21)) >> 22;   // FixedPtCast<int, uchar, INTER_RESIZE_COEF_BITS * 2>
+    }
+    dst[c] = (uint8_t)min(max(v, 0), 255);
+  }
+}
+
+// ---- host side of the tap tables: OpenCV's expressions in OpenCV's precision -------------------------
+#if defined(__GNUC__) && !defined(__clang__)
+#define STB_NO_CONTRACT __attribute__((optimize("fp-contract=off")))
+#else
+#define STB_NO_CONTRACT
+#endif
+
+static STB_NO_CONTRACT void cubic_coeffs(float x, float* c) {          // cv::interpolateCubic
+  const float A = -0.75f;
+  c[0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
+  c[1] = ((A + 2) * x - (A + 3)) * x * x + 1;
+  c[2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
+  c[3] = 1.f - c[0] - c[1] - c[2];
+}
+
+static STB_NO_CONTRACT void lanczos4_coeffs(float x, float* c) {       // cv::interpolateLanczos4
+  static const double s45 = 0.70710678118654752440;
+  static const double cs[][2] = {{1, 0}, {-s45, -s45}, {0, 1}, {s45, -s45}, {-1, 0}, {s45, s45}, {0, -1}, {-s45, s45}};
+  if (x < 1.1920928955078125e-07f) {                                   // FLT_EPSILON
+    for (int i = 0; i < 8; ++i) c[i] = 0.f;
+    c[3] = 1.f;
+    return;
+  }
+  float sum = 0.f;
+  const double y0 = -(x + 3) * 3.1415926535897932384626433832795 * 0.25, s0 = std::sin(y0), c0 = std::cos(y0);
+  for (int i = 0; i < 8; ++i) {
+    const double y = -(x + 3 - i) * 3.1415926535897932384626433832795 * 0.25;
+    c[i] = (float)((cs[i][0] * s0 + cs[i][1] * c0) / (y * y));
+    sum += c[i];
+  }
+  sum = 1.f / sum;
+  for (int i = 0; i < 8; ++i) c[i] *= sum;
+}
+
+static STB_NO_CONTRACT void build_taps(int dn, int sn, int K, bool cubic, std::vector<int>& ofs, std::vector<short>& al) {
+  const double scale = 1. / ((double)dn / sn);
+  ofs.resize(dn);
+  al.resize((size_t)dn * K);
+  for (int d = 0; d < dn; ++d) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    const int s0 = (int)std::floor(f);
+    f -= s0;
+    float c[8];
+    if (cubic) cubic_coeffs(f, c); else lanczos4_coeffs(f, c);
+    ofs[d] = s0 - (K / 2 - 1);
+    for (int k = 0; k < K; ++k) {
+      const float v = c[k] * 2048.f;                                   // saturate_cast<short>(cbuf[k] * INTER_RESIZE_COEF_SCALE)
+      const long r = std::lrint(v);                                    // round half to even (default rounding mode)
+      al[(size_t)d * K + k] = (short)(r < -32768 ? -32768 : (r > 32767 ? 32767 : r));
+    }
+  }
+}
+
 }  // namespace stb
 
 using namespace stb;
@@ -212,8 +331,8 @@ int stb_resize_target(int frame_w, int frame_h, int width, int height, int min_f
 
 int stb_resize_interp_code(const char* name) {
   if (!name || !*name) return kInterpLinear;
-  const char* names[] = {"INTER_LINEAR", "INTER_NEAREST", "INTER_AREA"};
-  for (int i = 0; i < 3; ++i) {
+  const char* names[] = {"INTER_LINEAR", "INTER_NEAREST", "INTER_AREA", "INTER_CUBIC", "INTER_LANCZOS4"};
+  for (int i = 0; i < 5; ++i) {
     const char* a = names[i];
     const char* b = name;
     while (*a && *a == *b) { ++a; ++b; }
@@ -245,11 +364,40 @@ int stb_resize_u8(const uint8_t* const* d_src, int n, int src_w, int src_h, int 
     set_error("stb_resize_u8: %d channels not supported (1, 3, 4)", channels);
     return STB_ERR_UNSUPPORTED;
   }
-  if (interp != kInterpLinear && interp != kInterpNearest && interp != kInterpArea) {
-    set_error("stb_resize_u8: interpolation %d is not implemented (INTER_LINEAR, INTER_NEAREST, INTER_AREA)", interp);
+  if (interp < kInterpLinear || interp > kInterpLanczos4) {
+    set_error("stb_resize_u8: interpolation %d is not implemented (INTER_LINEAR, INTER_NEAREST, INTER_AREA, INTER_CUBIC, INTER_LANCZOS4)", interp);
     return STB_ERR_UNSUPPORTED;
   }
   cudaStream_t s = (cudaStream_t)stream;
+  // INTER_CUBIC / INTER_LANCZOS4: tap tables built here, uploaded and released in stream order
+  const bool taps = interp == kInterpCubic || interp == kInterpLanczos4;
+  const int K = interp == kInterpCubic ? 4 : 8;
+  int* d_tab = nullptr;
+  const int *d_xofs = nullptr, *d_yofs = nullptr;
+  const short *d_xa = nullptr, *d_ya = nullptr;
+  if (taps) {
+    std::vector<int> xo, yo;
+    std::vector<short> xa, ya;
+    build_taps(dst_w, src_w, K, interp == kInterpCubic, xo, xa);
+    build_taps(dst_h, src_h, K, interp == kInterpCubic, yo, ya);
+    // one allocation: [xofs | yofs | xa | ya]
+    const size_t n_int = (size_t)dst_w + dst_h, n_short = ((size_t)dst_w + dst_h) * K;
+    std::vector<int> host(n_int + (n_short + 1) / 2);
+    std::copy(xo.begin(), xo.end(), host.begin());
+    std::copy(yo.begin(), yo.end(), host.begin() + dst_w);
+    short* hs = reinterpret_cast<short*>(host.data() + n_int);
+    std::copy(xa.begin(), xa.end(), hs);
+    std::copy(ya.begin(), ya.end(), hs + (size_t)dst_w * K);
+    STB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_tab), host.size() * sizeof(int), s));
+    // pageable source: the runtime stages it before returning, so `host` may go out of scope
+    cudaError_t e = cudaMemcpyAsync(d_tab, host.data(), host.size() * sizeof(int), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) { cudaFreeAsync(d_tab, s); return cuda_fail(e, "stb_resize_u8: tap table upload"); }
+    d_xofs = d_tab;
+    d_yofs = d_tab + dst_w;
+    d_xa = reinterpret_cast<const short*>(d_tab + n_int);
+    d_ya = d_xa + (size_t)dst_w * K;
+  }
+  const int vec_elems = interp == kInterpCubic ? (dst_w * channels / 8) * 8 : 0;
   const double scale_x = 1. / ((double)dst_w / src_w), scale_y = 1. / ((double)dst_h / src_h);
   // cv::resize: iscale = saturate_cast<int>(scale) (round half even); "fast area" when both are integers
   const int isx = (int)std::nearbyint(scale_x), isy = (int)std::nearbyint(scale_y);
@@ -267,12 +415,25 @@ int stb_resize_u8(const uint8_t* const* d_src, int n, int src_w, int src_h, int 
       b.p[i] = d_dst[base + i];
     }
     const dim3 grid(ceil_div(dst_w, 32), ceil_div(dst_h, 8), m);
-    if (interp == kInterpNearest) STB_RESIZE_DISPATCH(resize_nearest_u8_kernel, src_w, src_h, dst_w, dst_h, scale_x, scale_y);
+    if (taps) {
+      if (K == 4) {
+        if (channels == 3) stb_launch(resize_taps_u8_kernel<3, 4>, grid, dim3(256), 0, s, a, b, src_w, src_h, dst_w, dst_h, d_xofs, d_xa, d_yofs, d_ya, vec_elems);
+        else if (channels == 1) stb_launch(resize_taps_u8_kernel<1, 4>, grid, dim3(256), 0, s, a, b, src_w, src_h, dst_w, dst_h, d_xofs, d_xa, d_yofs, d_ya, vec_elems);
+        else stb_launch(resize_taps_u8_kernel<4, 4>, grid, dim3(256), 0, s, a, b, src_w, src_h, dst_w, dst_h, d_xofs, d_xa, d_yofs, d_ya, vec_elems);
+      } else {
+        if (channels == 3) stb_launch(resize_taps_u8_kernel<3, 8>, grid, dim3(256), 0, s, a, b, src_w, src_h, dst_w, dst_h, d_xofs, d_xa, d_yofs, d_ya, vec_elems);
+        else if (channels == 1) stb_launch(resize_taps_u8_kernel<1, 8>, grid, dim3(256), 0, s, a, b, src_w, src_h, dst_w, dst_h, d_xofs, d_xa, d_yofs, d_ya, vec_elems);
+        else stb_launch(resize_taps_u8_kernel<4, 8>, grid, dim3(256), 0, s, a, b, src_w, src_h, dst_w, dst_h, d_xofs, d_xa, d_yofs, d_ya, vec_elems);
+      }
+    }
+    else if (interp == kInterpNearest) STB_RESIZE_DISPATCH(resize_nearest_u8_kernel, src_w, src_h, dst_w, dst_h, scale_x, scale_y);
     else if (interp == kInterpArea && down && int_scale) STB_RESIZE_DISPATCH(resize_area_int_u8_kernel, src_w, dst_w, dst_h, isx, isy);
     else if (interp == kInterpArea && down) STB_RESIZE_DISPATCH(resize_area_u8_kernel, src_w, src_h, dst_w, dst_h, scale_x, scale_y);
     else STB_RESIZE_DISPATCH(resize_linear_u8_kernel, src_w, src_h, dst_w, dst_h, scale_x, scale_y, area2x, interp == kInterpArea ? 1 : 0);
+    if (cudaPeekAtLastError() != cudaSuccess && d_tab) cudaFreeAsync(d_tab, s);
     STB_CHECK_LAUNCH("resize kernel");
   }
+  if (d_tab) STB_CUDA(cudaFreeAsync(d_tab, s));
   return STB_OK;
 }
 

@@ -89,18 +89,18 @@ class ResizeKernelGPU : public BatchedKernel {
     args_ = ResizeArgsLite();
     if (!parse_resize_args(args, &args_)) RESULT_ERROR(&valid_, "Resize: could not parse ResizeArgs");
     // resize_kernel.cpp:31-35: names outside its INTERP_TYPES table silently mean INTER_LINEAR.  Of the
-    // names inside the table, INTER_LINEAR / INTER_NEAREST / INTER_AREA are implemented; the rest fail
-    // validate() instead of silently producing a different interpolation.
+    // names inside the table, the five interpolation modes (INTER_NEAREST / LINEAR / CUBIC / AREA / LANCZOS4) are
+    // implemented; the rest (INTER_MAX, WARP_*: flag values, not modes) fail validate() instead of silently
+    // producing a different interpolation.
     interp_ = 0;
     const int code = stb_resize_interp_code(args_.interpolation.c_str());
     if (code >= 0) {
       interp_ = code;
     } else {
-      static const char* const kKnownUnimplemented[] = {"INTER_CUBIC", "INTER_LANCZOS4", "INTER_MAX", "WARP_FILL_OUTLIERS",
-                                                        "WARP_INVERSE_MAP"};
+      static const char* const kKnownUnimplemented[] = {"INTER_MAX", "WARP_FILL_OUTLIERS", "WARP_INVERSE_MAP"};
       for (const char* name : kKnownUnimplemented)
         if (args_.interpolation == name)
-          RESULT_ERROR(&valid_, "Resize (B200): interpolation %s is not implemented (INTER_LINEAR, INTER_NEAREST, INTER_AREA)",
+          RESULT_ERROR(&valid_, "Resize (B200): interpolation %s is not implemented (INTER_NEAREST, INTER_LINEAR, INTER_CUBIC, INTER_AREA, INTER_LANCZOS4)",
                        args_.interpolation.c_str());
     }
   }

@@ -22,7 +22,7 @@ from . import _lib
 HIST_BINS = 16       # histogram_kernel_cpu.cpp:8
 FLOW_HIST_BINS = 64  # flow_histogram_kernel_cpu.cpp:9
 # names of resize_kernel.cpp:9-20's table without a kernel here
-RESIZE_TABLE_UNIMPLEMENTED = ('INTER_CUBIC', 'INTER_LANCZOS4', 'INTER_MAX', 'WARP_FILL_OUTLIERS', 'WARP_INVERSE_MAP')
+RESIZE_TABLE_UNIMPLEMENTED = ('INTER_MAX', 'WARP_FILL_OUTLIERS', 'WARP_INVERSE_MAP')   # flag values, not interpolation modes
 
 
 def _torch():
@@ -192,8 +192,10 @@ def resize_target(frame_w, frame_h, width=0, height=0, min=False, preserve_aspec
 
 def resize(frames, width=0, height=0, min=False, preserve_aspect=False, interpolation='INTER_LINEAR', stream=None):
     """Resize op (scannertools_cpp/imgproc/resize_kernel.cpp:22-105) on uint8 frames: n frames ->
-    [n, height, width, C], bit-exact with cv::resize for INTER_LINEAR (the default), INTER_NEAREST and
-    INTER_AREA; the other names of the reference's table (:9-20) raise NotImplementedError."""
+    [n, height, width, C], bit-exact with cv::resize for INTER_LINEAR (the default), INTER_NEAREST,
+    INTER_AREA, INTER_LANCZOS4 and INTER_CUBIC (OpenCV's own code path; builds that dispatch 8-bit cubic to
+    IPP differ from it by one grey level on ~5 % of pixels).  The remaining names of the reference's table
+    (:9-20: INTER_MAX, WARP_*, flag values rather than modes) raise NotImplementedError."""
     torch = _torch()
     lib = _lib.load()
     interp = lib.stb_resize_interp_code((interpolation or '').encode())
@@ -201,7 +203,7 @@ def resize(frames, width=0, height=0, min=False, preserve_aspect=False, interpol
         # resize_kernel.cpp:31-35: names outside the reference's INTERP_TYPES table silently mean INTER_LINEAR
         # (mirrored, like ResizeKernelGPU does); names INSIDE the table that are not implemented here raise
         if interpolation in RESIZE_TABLE_UNIMPLEMENTED:
-            raise NotImplementedError('Resize: INTER_LINEAR, INTER_NEAREST and INTER_AREA are implemented (got %r)' % (interpolation,))
+            raise NotImplementedError('Resize: INTER_LINEAR, INTER_NEAREST, INTER_AREA, INTER_CUBIC and INTER_LANCZOS4 are implemented (got %r)' % (interpolation,))
         interp = lib.stb_resize_interp_code(b'INTER_LINEAR')
     if isinstance(frames, torch.Tensor) and frames.dim() == 3:
         frames = frames.unsqueeze(0)

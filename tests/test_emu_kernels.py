@@ -157,9 +157,9 @@ def test_emu_resize_bit_exact(emu):
         assert np.array_equal(out, restate.resize(img, dw, dh)), (sw, sh, dw, dh, cn)
     # the other interpolation names of ResizeArgs: nearest, area (integer factors, general tables,
     # up-scaled / mixed axes), 1/3/4 channels, degenerate sizes
-    codes = {n: emu.stb_resize_interp_code(n.encode()) for n in ('INTER_LINEAR', 'INTER_NEAREST', 'INTER_AREA')}
-    assert codes == {'INTER_LINEAR': 0, 'INTER_NEAREST': 1, 'INTER_AREA': 2}
-    assert emu.stb_resize_interp_code(b'') == 0 and emu.stb_resize_interp_code(b'INTER_CUBIC') == -1
+    codes = {n: emu.stb_resize_interp_code(n.encode()) for n in ('INTER_LINEAR', 'INTER_NEAREST', 'INTER_AREA', 'INTER_CUBIC', 'INTER_LANCZOS4')}
+    assert codes == {'INTER_LINEAR': 0, 'INTER_NEAREST': 1, 'INTER_AREA': 2, 'INTER_CUBIC': 3, 'INTER_LANCZOS4': 4}
+    assert emu.stb_resize_interp_code(b'') == 0 and emu.stb_resize_interp_code(b'INTER_MAX') == -1
     for (sh, sw, dh, dw) in [(108, 192, 24, 43), (90, 160, 37, 71), (72, 128, 24, 43), (60, 90, 20, 30), (64, 96, 16, 24),
                              (40, 60, 20, 30), (24, 43, 108, 192), (30, 40, 60, 20), (30, 40, 15, 80), (7, 5, 31, 33),
                              (33, 47, 1, 1), (1, 1, 5, 7)]:

@@ -231,8 +231,32 @@ def test_resize_goldens_and_pipeline_size(torch, ops, golden):
         for (tw, th) in [(300, 200), (64, 200), (300, 31), (131, 97), (1, 1)]:
             out = ops.resize(dev(torch, small), width=tw, height=th, interpolation=name).cpu().numpy()[0]
             assert np.array_equal(out, (cvo or restate).resize(small, tw, th, name)), (name, tw, th)
+    # INTER_CUBIC / INTER_LANCZOS4: host-built tap tables, bit-exact with the restatement (pinned to OpenCV's own
+    # code path in tests/test_oracle.py) and with cv2 itself when its IPP dispatch is off; <= 1 grey level from IPP
+    for name in ('INTER_CUBIC', 'INTER_LANCZOS4'):
+        for (tw, th) in [(426, 240), (960, 540)]:
+            out = ops.resize(dev(torch, fr[:1]), width=tw, height=th, interpolation=name).cpu().numpy()[0]
+            assert np.array_equal(out, restate.resize(fr[0], tw, th, name)), (name, tw, th)
+        for (tw, th) in [(300, 200), (64, 200), (300, 31), (131, 97), (1, 1), (43, 29)]:
+            out = ops.resize(dev(torch, small), width=tw, height=th, interpolation=name).cpu().numpy()[0]
+            assert np.array_equal(out, restate.resize(small, tw, th, name)), (name, tw, th)
+            if cvo is not None:
+                import cv2
+                ipp0 = cv2.ipp.useIPP()
+                try:
+                    cv2.ipp.setUseIPP(False)
+                    assert np.array_equal(out, cv2.resize(small, (tw, th), interpolation=getattr(cv2, name))), (name, tw, th)
+                    cv2.ipp.setUseIPP(True)
+                    d = np.abs(out.astype(int) - cv2.resize(small, (tw, th), interpolation=getattr(cv2, name)).astype(int))
+                    assert d.max() <= 1, (name, tw, th)
+                finally:
+                    cv2.ipp.setUseIPP(ipp0)
+    gray1 = np.ascontiguousarray(small[..., :1])
+    for name in ('INTER_CUBIC', 'INTER_LANCZOS4'):
+        out = ops.resize(dev(torch, gray1), width=77, height=50, interpolation=name).cpu().numpy()[0]
+        assert np.array_equal(out[..., 0], restate.resize(gray1[..., 0], 77, 50, name).reshape(50, 77)), name
     with pytest.raises(NotImplementedError):
-        ops.resize(dev(torch, fr[:1]), width=10, height=10, interpolation='INTER_CUBIC')
+        ops.resize(dev(torch, fr[:1]), width=10, height=10, interpolation='INTER_MAX')
 
 
 def test_convert_color_and_hsv_histogram(torch, ops, golden):

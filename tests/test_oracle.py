@@ -165,6 +165,33 @@ def test_restate_resize_interpolations_vs_cv2():
                 assert np.array_equal(restate.resize(src, dw, dh, name), ref), (sh, sw, dh, dw, cn, name)
 
 
+def test_restate_resize_cubic_lanczos_vs_cv2():
+    """INTER_CUBIC / INTER_LANCZOS4 of the restatement against OpenCV's own implementation
+    (cv2.ipp.setUseIPP(False)): bit-exact, including the float vector path / integer tail split of the
+    cubic vertical pass (rows whose W * cn is not a multiple of 8).  With IPP dispatch on (this wheel's
+    default) 8-bit cubic comes from IPP and may differ from OpenCV's own code by one grey level; Lanczos4
+    has no IPP path."""
+    cv2 = pytest.importorskip('cv2')
+    rng = np.random.default_rng(4)
+    ipp0 = cv2.ipp.useIPP()
+    try:
+        for (sh, sw, dh, dw) in [(48, 64, 30, 41), (37, 53, 80, 111), (120, 160, 60, 80), (270, 480, 240, 426), (33, 47, 70, 21),
+                                 (24, 43, 108, 192), (7, 5, 31, 33), (50, 50, 50, 50), (33, 47, 1, 1), (1, 1, 5, 7), (3, 2, 9, 10)]:
+            for cn in (1, 3, 4):
+                src = rng.integers(0, 256, (sh, sw, cn), dtype=np.uint8)
+                src = src[..., 0] if cn == 1 else src
+                for name in ('INTER_CUBIC', 'INTER_LANCZOS4'):
+                    mine = restate.resize(src, dw, dh, name)
+                    cv2.ipp.setUseIPP(False)
+                    ref = cv2.resize(src, (dw, dh), interpolation=getattr(cv2, name))
+                    assert np.array_equal(mine.reshape(ref.shape), ref), (sh, sw, dh, dw, cn, name)
+                    cv2.ipp.setUseIPP(True)
+                    ref_ipp = cv2.resize(src, (dw, dh), interpolation=getattr(cv2, name))
+                    assert np.abs(mine.reshape(ref.shape).astype(int) - ref_ipp.astype(int)).max() <= 1, (sh, sw, dh, dw, cn, name)
+    finally:
+        cv2.ipp.setUseIPP(ipp0)
+
+
 def test_cv2_fast_pyramids_is_a_no_op_on_cpu():
     """stb_farneback_params.fast_pyramids is accepted and ignored: OpenCV's CPU Farneback (the
     parity target) gives bit-identical flow with fastPyramids true or false."""

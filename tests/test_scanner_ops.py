@@ -99,14 +99,15 @@ def test_resize_kernel_class_with_serialized_args(shim):
         assert np.array_equal(got[i], restate.resize(fr[i], ow.value, oh.value))
     # interpolation names: implemented ones are honoured, names outside the reference's table mean
     # INTER_LINEAR (resize_kernel.cpp:31-35), table names that are not implemented fail validate()
-    for name, oracle_name in ((b'INTER_AREA', 'INTER_AREA'), (b'INTER_NEAREST', 'INTER_NEAREST'), (b'bogus', 'INTER_LINEAR')):
+    for name, oracle_name in ((b'INTER_AREA', 'INTER_AREA'), (b'INTER_NEAREST', 'INTER_NEAREST'), (b'INTER_CUBIC', 'INTER_CUBIC'),
+                              (b'INTER_LANCZOS4', 'INTER_LANCZOS4'), (b'bogus', 'INTER_LINEAR')):
         args = _resize_args(width=107, height=60, interpolation=name)
         rc = shim.stb_shim_resize(P(fr), 2, 480, 270, 3, args, len(args), P(out), out.size, C.byref(ow), C.byref(oh), 0)
         assert rc == 0 and (ow.value, oh.value) == (107, 60)
         got = out[:2 * 60 * 107 * 3].reshape(2, 60, 107, 3)
         for i in range(2):
             assert np.array_equal(got[i], restate.resize(fr[i], 107, 60, oracle_name)), name
-    bad = _resize_args(width=10, height=10, interpolation=b'INTER_CUBIC')
+    bad = _resize_args(width=10, height=10, interpolation=b'INTER_MAX')
     assert shim.stb_shim_resize(P(fr), 1, 480, 270, 3, bad, len(bad), P(out), out.size, C.byref(ow), C.byref(oh), 0) == -4
 
 
