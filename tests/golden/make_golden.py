@@ -18,8 +18,33 @@ from scannertools_b200 import synth  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+def make_resize_taps():
+    """INTER_CUBIC / INTER_LANCZOS4 goldens from OpenCV's OWN resize code: cv2.ipp.setUseIPP(False), because this
+    wheel otherwise hands 8-bit cubic to IPP (a different arithmetic, +-1 grey level).  `python make_golden.py resize_taps`
+    writes only this file."""
+    meta = dict(cv2=cv2.__version__, numpy=np.__version__, ipp='off')
+    rng = np.random.default_rng(31)
+    ipp0 = cv2.ipp.useIPP()
+    cv2.ipp.setUseIPP(False)
+    try:
+        rs = {}
+        for name, (sh, sw, dh, dw, cn) in {'down_frac': (135, 240, 60, 107, 3), 'up': (37, 53, 80, 111, 3), 'half': (120, 160, 60, 80, 3),
+                                           'gray_mixed': (33, 47, 70, 21, 1), 'rgba': (40, 30, 25, 64, 4), 'tiny': (3, 2, 9, 10, 3)}.items():
+            img = rng.integers(0, 256, (sh, sw, cn) if cn > 1 else (sh, sw), dtype=np.uint8)
+            rs['in_' + name] = img
+            for interp in ('INTER_CUBIC', 'INTER_LANCZOS4'):
+                rs['out_%s_%s' % (interp, name)] = cv2.resize(img, (dw, dh), interpolation=getattr(cv2, interp))
+    finally:
+        cv2.ipp.setUseIPP(ipp0)
+    np.savez_compressed(os.path.join(HERE, 'resize_taps.npz'), meta=str(meta), **rs)
+
+
 def main():
+    if sys.argv[1:] == ['resize_taps']:
+        make_resize_taps()
+        return
     meta = dict(cv2=cv2.__version__, numpy=np.__version__)
+    make_resize_taps()
 
     # C1: ShotDetection clip -- 1000 frames 640x360, 7 planted cuts, seed 5 (SURVEY §8d)
     clip, cuts = synth.cut_clip(5, 1000, 360, 640, n_cuts=7)

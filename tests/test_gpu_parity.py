@@ -251,6 +251,14 @@ def test_resize_goldens_and_pipeline_size(torch, ops, golden):
                     assert d.max() <= 1, (name, tw, th)
                 finally:
                     cv2.ipp.setUseIPP(ipp0)
+    g = golden('resize_taps.npz')
+    for nme in [k[3:] for k in g.files if k.startswith('in_')]:
+        for name in ('INTER_CUBIC', 'INTER_LANCZOS4'):
+            src, ref = g['in_' + nme], g['out_%s_%s' % (name, nme)]
+            if src.ndim == 2:
+                src, ref = src[..., None], ref[..., None]
+            out = ops.resize(dev(torch, src), width=ref.shape[1], height=ref.shape[0], interpolation=name).cpu().numpy()[0]
+            assert np.array_equal(out, ref), (name, nme)
     gray1 = np.ascontiguousarray(small[..., :1])
     for name in ('INTER_CUBIC', 'INTER_LANCZOS4'):
         out = ops.resize(dev(torch, gray1), width=77, height=50, interpolation=name).cpu().numpy()[0]

@@ -192,6 +192,14 @@ def test_restate_resize_cubic_lanczos_vs_cv2():
         cv2.ipp.setUseIPP(ipp0)
 
 
+def test_restate_resize_cubic_lanczos_goldens(golden):
+    g = golden('resize_taps.npz')
+    for nme in [k[3:] for k in g.files if k.startswith('in_')]:
+        for interp in ('INTER_CUBIC', 'INTER_LANCZOS4'):
+            ref = g['out_%s_%s' % (interp, nme)]
+            assert np.array_equal(restate.resize(g['in_' + nme], ref.shape[1], ref.shape[0], interp), ref), (interp, nme)
+
+
 def test_cv2_fast_pyramids_is_a_no_op_on_cpu():
     """stb_farneback_params.fast_pyramids is accepted and ignored: OpenCV's CPU Farneback (the
     parity target) gives bit-identical flow with fastPyramids true or false."""
