@@ -1,14 +1,14 @@
 set -x
-python -m pytest tests -m gpu -x -q -k "resize or scanner or kernel_class or histogram_goldens" 2>&1 | tail -5
-cat > /tmp/rs.py <<'PY'
-import sys, numpy as np, torch
-sys.path.insert(0, '.')
-from scannertools_b200 import ops
-fr = torch.randint(0, 256, (2, 270, 480, 3), dtype=torch.uint8, device='cuda')
-for name in ('INTER_CUBIC', 'INTER_LANCZOS4'):
-    for (tw, th) in [(213, 120), (700, 301), (1, 1)]:
-        ops.resize(fr, width=tw, height=th, interpolation=name)
-torch.cuda.synchronize()
-print('ok')
+mkdir -p gpurun_out
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/r2f_bench_n8.json 2> gpurun_out/r2f_bench_n8.err
+tail -c 300 gpurun_out/r2f_bench_n8.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2f_bench_n8.json').read().strip().splitlines()[-1])
+print(d['value'], d['e2e']['value'], d['e2e'].get('copy_only'), d['roofline']['frac'], d['clocks'])
+for k,v in d.get('extra',{}).items():
+    if 'value' in v: print(k, v.get('value'), v.get('roofline',{}).get('frac'), v.get('e2e',{}).get('value'), v.get('shard_check'))
+    else:
+        for kk,vv in v.items(): print(k,kk,vv.get('value'))
+print(d.get('shard_check'))
 PY
-compute-sanitizer --tool memcheck python /tmp/rs.py 2>&1 | tail -4
