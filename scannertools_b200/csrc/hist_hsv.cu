@@ -4,8 +4,12 @@
 // written: each RGB byte is read once, converted in registers with OpenCV's integer tables
 // (hsv.cuh) and counted.  Result == stb_hist_rgb16(stb_convert_color_u8(frame, RGB2HSV)).
 //
-// Counting uses the same privatisation as hist.cu (per warp AND per lane, bank == lane), with 44
-// planes per warp instead of 48: H < 180 only reaches bins 0..11.
+// Counting uses per-LANE private counters (bank == lane), one table of 44 planes per block (H < 180 only
+// reaches bins 0..11); updates of different warps are different instructions and serialise in the atomic
+// unit anyway.  The two division tables of OpenCV's integer HSV (sdiv[v], hdiv[diff]) are replicated per
+// lane as well -- [256][32] words each, 64 KB -- so a look-up is one conflict-free wavefront whatever the 32
+// indices are: with one shared copy the random indices of a warp collided on banks, 3.1 wavefronts per
+// look-up, which was two thirds of this kernel's shared-memory traffic (round 2 ncu: 12.9 M of 19.7 M).
 #include "stb_rt.h"
 #include "hsv.cuh"
 
@@ -22,11 +26,11 @@ struct HsvStrideAddr {
 };
 
 constexpr int kHsvThreads = 384;
-constexpr int kHsvWarps = kHsvThreads / 32;
 constexpr int kHsvPlanes = 12 + 16 + 16;                       // H bins 0..11, S, V
 constexpr int kHsvPlaneS = 12, kHsvPlaneV = 28;
-constexpr int kHsvTableWords = kHsvWarps * kHsvPlanes * 32;    // 16 896 words = 66 KB
-constexpr int kHsvSmemBytes = kHsvTableWords * 4 + 2 * 256 * 4;  // + sdiv, hdiv
+constexpr int kHsvTableWords = kHsvPlanes * 32;                // 1 408 words = 5.5 KB of counters
+constexpr int kHsvDivWords = 256 * 32;                         // one division table, replicated per lane: 32 KB
+constexpr int kHsvSmemBytes = (kHsvTableWords + 2 * kHsvDivWords) * 4;   // 71 168 B: three blocks per SM
 constexpr int kHsvGroupPx = 16;                                // pixels per thread per step (48 bytes)
 
 __device__ __forceinline__ int hsv_byte(unsigned w, int k) {
@@ -46,11 +50,11 @@ struct HsvSmem {
   const int* hdiv;
   template <int SHIFT>
   __device__ __forceinline__ void inc(int plane, int x) const { atomicAdd(my + (plane + (x >> SHIFT)) * 32, 1u); }
-  __device__ __forceinline__ int s_div(int v) const { return sdiv[v]; }
-  __device__ __forceinline__ int h_div(int d) const { return hdiv[d]; }
+  __device__ __forceinline__ int s_div(int v) const { return sdiv[v * 32]; }
+  __device__ __forceinline__ int h_div(int d) const { return hdiv[d * 32]; }
 };
-__device__ __forceinline__ HsvSmem hsv_smem(unsigned* sh, unsigned warp, unsigned lane, const int* sdiv, const int* hdiv) {
-  return HsvSmem{sh + warp * (kHsvPlanes * 32) + lane, sdiv, hdiv};
+__device__ __forceinline__ HsvSmem hsv_smem(unsigned* sh, unsigned lane, const int* sdiv, const int* hdiv) {
+  return HsvSmem{sh + lane, sdiv + lane, hdiv + lane};
 }
 #else
 struct HsvSmem {
@@ -65,19 +69,19 @@ struct HsvSmem {
   }
   __device__ __forceinline__ int s_div(int v) const {
     int r;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(r) : "r"(sdiv + ((unsigned)v << 2)));
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(r) : "r"(sdiv + ((unsigned)v << 7)));
     return r;
   }
   __device__ __forceinline__ int h_div(int d) const {
     int r;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(r) : "r"(hdiv + ((unsigned)d << 2)));
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(r) : "r"(hdiv + ((unsigned)d << 7)));
     return r;
   }
 };
-__device__ __forceinline__ HsvSmem hsv_smem(unsigned* sh, unsigned warp, unsigned lane, const int* sdiv, const int* hdiv) {
+__device__ __forceinline__ HsvSmem hsv_smem(unsigned* sh, unsigned lane, const int* sdiv, const int* hdiv) {
   const unsigned base = (unsigned)__cvta_generic_to_shared(sh);
-  return HsvSmem{base + (warp * (kHsvPlanes * 32) + lane) * 4u, (unsigned)__cvta_generic_to_shared(sdiv),
-                 (unsigned)__cvta_generic_to_shared(hdiv)};
+  return HsvSmem{base + lane * 4u, (unsigned)__cvta_generic_to_shared(sdiv) + lane * 4u,
+                 (unsigned)__cvta_generic_to_shared(hdiv) + lane * 4u};
 }
 #endif
 
@@ -130,19 +134,30 @@ hist_hsv16_kernel(Addr addr, unsigned long long npx, int32_t* __restrict__ out, 
   unsigned frame, part, nparts;
   flat_grid_decode(blockIdx.x, base_blocks, rem, frame, part, nparts);
   STB_DYN_SMEM(unsigned, sh);
-  int* sdiv = reinterpret_cast<int*>(sh + kHsvTableWords);
-  int* hdiv = sdiv + 256;
-  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  int* sdiv = reinterpret_cast<int*>(sh + kHsvTableWords);   // [256][32]
+  int* hdiv = sdiv + kHsvDivWords;                           // [256][32]
+  const unsigned tid = threadIdx.x, lane = tid & 31u;
   {
     uint4* z = reinterpret_cast<uint4*>(sh);
     for (unsigned i = tid; i < kHsvTableWords / 4; i += kHsvThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
   }
-  hsv_tables_init(sdiv, hdiv, tid);
+  if (tid < 256u) {
+    // thread i computes entry i of both tables (hsv.cuh) and writes it into all 32 lane slots
+    const int i = (int)tid;
+    const int sv = i ? __double2int_rn((double)(255 << 12) / (double)i) : 0;
+    const int hv = i ? __double2int_rn((double)(180 << 12) / (6.0 * (double)i)) : 0;
+    const int4 s4 = make_int4(sv, sv, sv, sv), h4 = make_int4(hv, hv, hv, hv);
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      reinterpret_cast<int4*>(sdiv + i * 32)[l] = s4;
+      reinterpret_cast<int4*>(hdiv + i * 32)[l] = h4;
+    }
+  }
   __syncthreads();
 
   const uint8_t* f = addr(frame);
   const bool aligned = (reinterpret_cast<uintptr_t>(f) & 15u) == 0;
-  const HsvSmem m = hsv_smem(sh, warp, lane, sdiv, hdiv);
+  const HsvSmem m = hsv_smem(sh, lane, sdiv, hdiv);
   const unsigned long long ngroups = npx / kHsvGroupPx;
   const unsigned long long gt = (unsigned long long)part * kHsvThreads + tid;
   const unsigned long long T = (unsigned long long)nparts * kHsvThreads;
@@ -168,18 +183,15 @@ hist_hsv16_kernel(Addr addr, unsigned long long npx, int32_t* __restrict__ out, 
   }
   __syncthreads();
 
-  // block reduce: 8 threads per output bin (bin = ch*16 + b), each sums 4 lanes x 12 warps
+  // block reduce: 8 threads per output bin (bin = ch*16 + b), each sums 4 lanes
   const unsigned bin = tid >> 3, rpart = tid & 7u;
   const unsigned ch = bin >> 4, b = bin & 15u;
   const bool live = !(ch == 0 && b >= 12u);                       // H bins 12..15 stay zero
   const unsigned plane = ch == 0 ? b : (ch == 1 ? kHsvPlaneS + b : kHsvPlaneV + b);
   unsigned s = 0;
   if (live) {
-#pragma unroll
-    for (int w = 0; w < kHsvWarps; ++w) {
-      const uint4 q = *reinterpret_cast<const uint4*>(sh + (w * kHsvPlanes + plane) * 32 + rpart * 4);
-      s += q.x + q.y + q.z + q.w;
-    }
+    const uint4 q = *reinterpret_cast<const uint4*>(sh + plane * 32 + rpart * 4);
+    s = q.x + q.y + q.z + q.w;
   }
   s += __shfl_xor_sync(0xffffffffu, s, 1);
   s += __shfl_xor_sync(0xffffffffu, s, 2);
