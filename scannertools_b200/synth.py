@@ -173,3 +173,22 @@ def textured_flow_field(seed, h, w, scale=6.0):
     f[5::43, ::47, 0] = 0.0
     f[::53, 7::59, 1] = 0.0
     return f
+
+
+def edge_flow_field(seed, h, w):
+    """A float32 h x w x 2 flow field for FlowHistogram binning tests: generic vectors of several scales, magnitudes
+    on and next to the integer bin edges, directions on and next to the 64 angle-bin edges (5.625 degrees apart),
+    and 16 tiny / huge / infinite / axis-aligned specials (no NaN: OpenCV bins cvFloor(NaN) garbage)."""
+    rng = np.random.default_rng(seed)
+    n = h * w
+    f = (rng.standard_normal((n, 2)) * rng.choice([0.3, 3.0, 12.0, 40.0], size=(n, 1))).astype(np.float32)
+    k = n // 8
+    ang = np.deg2rad(rng.integers(0, 64, k) * 5.625 + rng.choice([0.0, 1e-4, -1e-4, 3e-3, -3e-3], k))
+    mag = rng.uniform(0.1, 70.0, k)
+    f[:k] = np.stack([mag * np.cos(ang), mag * np.sin(ang)], 1).astype(np.float32)
+    m2 = rng.integers(0, 66, k).astype(np.float64) + rng.choice([0.0, 1e-6, -1e-6, 1e-4, -1e-4], k)
+    a2 = rng.uniform(0, 2 * np.pi, k)
+    f[k:2 * k] = np.stack([m2 * np.cos(a2), m2 * np.sin(a2)], 1).astype(np.float32)
+    f[2 * k:2 * k + 16] = np.array([[0, 0], [1e-20, 0], [0, -1e-20], [1e-8, 1e-8], [1e20, 1], [-1e20, -1e20], [np.inf, 1], [1, -np.inf],
+                                    [2, -2], [3, 4], [-3, 4], [0, 5], [0, -5], [64, 0], [-64, 0], [1e-7, -1e-30]], np.float32)
+    return np.ascontiguousarray(f.reshape(h, w, 2))

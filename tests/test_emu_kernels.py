@@ -331,3 +331,14 @@ def test_emu_flow_compensated_window_equals_global_gathers(emu, h, w, gen):
         res.append(flows)
     for i in range(2):
         assert np.array_equal(res[0][i], res[1][i]), i
+
+
+def test_emu_flow_histogram_fast_binning_randomised(emu):
+    """flow_bins_fast (approximate location + exact path inside the guard bands, magic-number rint / floor, trash
+    rows for dropped values) against the restatement on a field that mixes generic vectors, magnitudes on and next
+    to integers, directions on and next to the 64 angle-bin edges, tiny, huge and non-finite values."""
+    h, w = 192, 256
+    ff = synth.edge_flow_field(11, h, w)
+    out = np.zeros(128, np.int32)
+    assert emu.stb_flow_hist(_lib.ptr_table([ff.ctypes.data]), 1, w, h, P(out), None) == 0
+    assert np.array_equal(out.reshape(2, 64), restate.flow_histogram(ff))

@@ -676,3 +676,16 @@ def test_flow_compensated_window_equals_global_gathers(torch, ops, h, w, gen):
     b_flow, b_fh = win.execute_with_histogram(fr)
     assert torch.equal(a_flow, b_flow) and torch.equal(a_fh, b_fh)
     plain.close(); win.close()
+
+
+@pytest.mark.gpu
+def test_flow_histogram_fast_binning_randomised(torch, ops):
+    """The device's approximate bin location (MUFU.SQRT / MUFU.RCP) + exact path inside the guard bands against the
+    oracle on fields dense in values on and next to bin edges, tiny / huge / non-finite values included; also
+    against cv2 itself when it is importable."""
+    for seed, (h, w) in ((11, (192, 256)), (12, (1080, 1920))):
+        ff = synth.edge_flow_field(seed, h, w)
+        out = ops.flow_histogram(dev(torch, ff)).cpu().numpy()[0]
+        assert np.array_equal(out, restate.flow_histogram(ff)), seed
+        if cvo is not None:
+            assert np.array_equal(out, cvo.flow_histogram(ff)), seed
