@@ -38,6 +38,13 @@ def main():
             t = timeit(lambda: ops.histogram(fr))
             by = n * (3 * h * w + 192)
             print('hist %dx%d n=%d %s: %.3f ms  %.0f fps  %.1f GB/s  %.1f%% of measured HBM' % (w, h, n, kind, t * 1e3, n / t, by / t / 1e9, 100 * by / t / PEAK))
+    if 'framediff' in which:
+        # FrameDifference over a whole batch in one call: frames [1..n) against [0..n-1) (9WH bytes per frame: 2 reads + 1 write of 3WH)
+        for (h, w, n) in [(2160, 3840, 16), (1080, 1920, 64)]:
+            fr = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device='cuda')
+            t = timeit(lambda: ops.frame_difference(fr[:-1], fr[1:]))
+            by = (n - 1) * 9 * h * w
+            print('framediff %dx%d n=%d: %.3f ms %.0f fps %.1f GB/s %.1f%%' % (w, h, n - 1, t * 1e3, (n - 1) / t, by / t / 1e9, 100 * by / t / PEAK))
     if 'flowhist' in which:
         f = torch.randn((16, 1080, 1920, 2), device='cuda') * 5
         t = timeit(lambda: ops.flow_histogram(f))
